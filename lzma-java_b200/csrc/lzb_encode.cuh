@@ -1,0 +1,58 @@
+// lzb_encode.cuh -- device-side layout shared by the encoder kernels.
+//
+// The encoder is a three-kernel pipeline per wave of blocks (DESIGN.md
+// section "encoder"):
+//   1. lzb_mf_link_kernel   one warp per block: replays the three hash-head
+//                           tables of BinTree (LZ/BinTree.java:171-187,210)
+//                           32 positions at a time and records, per position,
+//                           the hash-2 / hash-3 candidates and the successor
+//                           in its hash-4 bucket;
+//   2. lzb_mf_tree_kernel   one thread per hash-4 bucket: inserts the
+//                           bucket's positions in order into its own binary
+//                           tree (BinTree.java:212-270) and emits every
+//                           position's (length, distance) list;
+//   3. lzb_parse_kernel     one warp per block: getOptimum / Backward /
+//                           encodeOne (LZMA/Encoder.java:335-1024) over the
+//                           precomputed lists, range coder included.
+// Steps 1-2 exploit that the match list of a position is a pure function of
+// the data: buckets own disjoint trees.
+#pragma once
+#include "lzb_common.cuh"
+#include "lzb_kernels.h"
+
+namespace lzb {
+
+constexpr uint32_t kHash2Size = 1u << 10;
+constexpr uint32_t kHash3Size = 1u << 16;
+constexpr uint32_t kBT2HashSize = 1u << 16;
+constexpr uint32_t kMfEmpty = 0xFFFFFFFFu;  // idx[] value of a position with no pairs
+constexpr int kPairDistBits = 23;            // pair = len << 23 | distance  (blocks <= 8 MiB)
+constexpr uint32_t kPairDistMask = (1u << kPairDistBits) - 1;
+constexpr uint64_t kEncMaxBlock = 1ull << kPairDistBits;
+constexpr uint32_t kHeadFlag = 0x80000000u;
+
+// Per-wave scratch; every per-block array is strided by the wave's largest block.
+struct MfWave {
+    const uint8_t* in;
+    const uint64_t* in_off;  // already offset to the wave's first block
+    const uint64_t* in_len;
+    uint32_t n_blocks;
+    uint32_t np;             // stride of per-position arrays = max block length + 1 (1-based positions)
+    uint32_t hash_stride;    // ints per block in `heads`
+    uint32_t pair_cap;       // u32 slots per block in `pairs`
+    uint32_t hash_mask;
+    uint32_t cyclic_size;    // dict + 1
+    int32_t fb, cut;
+    bool bt4;
+    uint32_t* heads;         // [n_blocks][hash_stride]  zeroed
+    uint32_t* next;          // [n_blocks][np]           zeroed; successor in the hash bucket
+    uint32_t* prev2;         // [n_blocks][np]           hash-2 candidate | kHeadFlag if first of its bucket
+    uint32_t* prev3;         // [n_blocks][np]
+    uint32_t* son;           // [n_blocks][2*np]         absolute-indexed tree links
+    uint32_t* idx;           // [n_blocks][np]           offset of the position's list in `pairs` or kMfEmpty
+    uint32_t* pairs;         // [n_blocks][pair_cap]     lists: count, then count packed pairs
+    uint32_t* pair_used;     // [n_blocks]               zeroed; bump allocator
+    uint32_t* overflow;      // [1]                      zeroed; set when a block ran out of pair slots
+};
+
+}  // namespace lzb

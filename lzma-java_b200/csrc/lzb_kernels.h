@@ -1,0 +1,65 @@
+// lzb_kernels.h -- internal interface between the C-ABI layer (lzb_api.cu)
+// and the sm_100a kernels.  Not installed; the public boundary is
+// include/lzma_b200.h.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define LZB_KERNEL_HEADER 13
+#define LZB_KERNEL_E_CAPACITY (-4)
+
+namespace lzb {
+
+// ---- decoder ---------------------------------------------------------------
+constexpr int kDecMaxWarps = 15;          // streams resident per SM
+constexpr size_t kDecSliceBytes = 15488;  // 15 * 15488 = 232 320 B <= 227 KB per CTA
+
+struct DecodeArgs {
+    const uint8_t* in;
+    const uint64_t* in_off;
+    const uint64_t* in_len;
+    uint8_t* out;
+    const uint64_t* out_off;
+    const uint64_t* out_cap;
+    uint64_t* out_len;
+    int32_t* status;
+    uint32_t n;
+    uint32_t* ticket;        // zeroed before launch
+    uint16_t* lit_scratch;   // literal models that do not fit shared memory
+    size_t lit_stride;       // in 16-bit slots, per warp
+};
+
+cudaError_t launch_decode_scan(const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len, uint32_t n,
+                               uint32_t* d_max_spill, cudaStream_t st);
+cudaError_t launch_decode(const DecodeArgs& a, bool lit_in_smem, int num_sms, cudaStream_t st, int* grid_out,
+                          int* warps_out);
+
+// ---- encoder ---------------------------------------------------------------
+struct EncodeArgs {
+    const uint8_t* in;
+    const uint64_t* in_off;
+    const uint64_t* in_len;
+    uint8_t* out;
+    const uint64_t* out_off;
+    const uint64_t* out_cap;
+    uint64_t* out_len;       // UINT64_MAX when out_cap was too small
+    uint32_t n;
+    uint64_t max_in_len;
+    int32_t dict_size, fb;
+    bool bt4;
+    int32_t lc, lp, pb;
+    bool eos, with_header;
+};
+
+// device scratch owned by an encoder handle (grow-only)
+struct EncScratch {
+    void* p = nullptr;
+    size_t cap = 0;
+    void release();
+};
+
+// Enqueue the whole encode pipeline for the batch on `st`.
+cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cudaStream_t st, int* launches);
+
+}  // namespace lzb

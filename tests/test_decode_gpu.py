@@ -1,0 +1,157 @@
+"""GPU parity for the batch decoder (Decoder.java:205-301) through the C ABI:
+streams produced by the CPU oracle (bit-identical to the reference encoder)
+and by liblzma must decode to the original bytes and agree with the oracle's
+decoder on return value and length, including corrupt and truncated input."""
+import lzma
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BASE = dict(dict_size=1 << 20, lc=3, lp=0, pb=2, fb=32, mf=1, eos=False)
+
+
+def _pack(streams):
+    off = np.zeros(len(streams), dtype=np.uint64)
+    ln = np.array([len(s) for s in streams], dtype=np.uint64)
+    if len(streams) > 1:
+        off[1:] = np.cumsum(ln)[:-1]
+    return np.frombuffer(b"".join(streams), dtype=np.uint8), off, ln
+
+
+def _decode_all(lzb, streams, sizes, slack=273):
+    arr, off, ln = _pack(streams)
+    cap = np.array([s + slack for s in sizes], dtype=np.uint64)
+    ooff = np.zeros(len(streams), dtype=np.uint64)
+    if len(streams) > 1:
+        ooff[1:] = np.cumsum(cap)[:-1]
+    dec = lzb.Decoder()
+    out, out_len, status = dec.code_batch(arr, off, ln, ooff, cap)
+    dec.close()
+    return [out[int(o): int(o) + int(l)].tobytes() for o, l in zip(ooff, out_len)], status
+
+
+def test_decode_oracle_streams_all_classes(lzb, oracle, corpus):
+    blocks, streams = [], []
+    for cls in range(4):
+        for k in range(6):
+            size = [1, 2, 777, 4096, 65536, 262144][k]
+            b = corpus.generate(size, 1, cls, 2, k).tobytes()
+            blocks.append(b)
+            streams.append(oracle.encode(b, oracle.props(**BASE), alone=True))
+    got, status = _decode_all(lzb, streams, [len(b) for b in blocks])
+    assert list(status) == [1] * len(blocks)
+    for g, b in zip(got, blocks):
+        assert g == b
+
+
+@pytest.mark.parametrize("kw", [{"lc": 0}, {"lc": 8}, {"lp": 1}, {"lp": 4}, {"pb": 0}, {"pb": 4}, {"pb": 3},
+                                {"lc": 4, "lp": 4, "pb": 4}, {"dict_size": 1}, {"dict_size": 4096},
+                                {"fb": 273, "dict_size": 1 << 23}, {"mf": 0}])
+def test_decode_property_variants(lzb, oracle, corpus, kw):
+    p = dict(BASE)
+    p.update(kw)
+    blocks = [corpus.generate(50000 + 1000 * c, 1, c, 5, 3).tobytes() for c in range(4)]
+    streams = [oracle.encode(b, oracle.props(**p), alone=True) for b in blocks]
+    got, status = _decode_all(lzb, streams, [len(b) for b in blocks])
+    assert list(status) == [1] * 4
+    assert got == blocks
+
+
+def test_decode_end_marker_and_unknown_size(lzb, oracle, corpus):
+    p = dict(BASE)
+    p["eos"] = True
+    blocks = [corpus.generate(30000, 1, c, 6, 0).tobytes() for c in range(4)] + [b""]
+    streams = [oracle.encode(b, oracle.props(**p), alone=True) for b in blocks]  # size field = -1
+    got, status = _decode_all(lzb, streams, [len(b) for b in blocks])
+    assert list(status) == [1] * 5 and got == blocks
+    # liblzma's encoder: a different parser, same format
+    filt = [{"id": lzma.FILTER_LZMA1, "dict_size": 1 << 20, "lc": 3, "lp": 0, "pb": 2, "nice_len": 64}]
+    streams = [lzma.compress(b, format=lzma.FORMAT_ALONE, filters=filt) for b in blocks]
+    got, status = _decode_all(lzb, streams, [len(b) for b in blocks])
+    assert list(status) == [1] * 5 and got == blocks
+
+
+def test_decode_mixed_properties_in_one_batch(lzb, oracle, corpus):
+    variants = [{}, {"lc": 8}, {"pb": 4}, {"lp": 2, "lc": 2}, {"eos": True}, {"dict_size": 1 << 16}]
+    blocks, streams = [], []
+    for i, kw in enumerate(variants * 3):
+        p = dict(BASE)
+        p.update(kw)
+        b = corpus.generate(20000 + 37 * i, 1, i % 4, 7, i).tobytes()
+        blocks.append(b)
+        streams.append(oracle.encode(b, oracle.props(**p), alone=True))
+    got, status = _decode_all(lzb, streams, [len(b) for b in blocks])
+    assert list(status) == [1] * len(blocks) and got == blocks
+
+
+def test_decode_corrupt_and_truncated_matches_oracle(lzb, oracle, corpus):
+    rng = np.random.default_rng(1234)
+    good = [oracle.encode(corpus.generate(20000, 1, c, 8, 0).tobytes(), oracle.props(**BASE), alone=True) for c in range(4)]
+    bad = []
+    for s in good:
+        a = bytearray(s)
+        bad.append(bytes(a[: len(a) // 2]))            # truncated: EOF reads as all ones (RangeDecoder.java:23,36)
+        for _ in range(3):                              # flipped payload bytes
+            b = bytearray(s)
+            i = int(rng.integers(13, len(b)))
+            b[i] ^= 1 << int(rng.integers(0, 8))
+            bad.append(bytes(b))
+        b = bytearray(s)
+        b[0] = 225                                      # pb = 5: SetDecoderProperties returns false
+        bad.append(bytes(b))
+        bad.append(bytes(s[:7]))                        # shorter than the header
+    sizes = [20000] * len(bad)
+    got, status = _decode_all(lzb, bad, sizes)
+    for i, s in enumerate(bad):
+        ok, ref = oracle.decode_alone(s, out_cap=20000 + 273)
+        assert int(status[i]) == (ok if ok >= 0 else lzb.LZB_E_CAPACITY), i
+        assert len(got[i]) == len(ref), i
+        if ok == 1:
+            assert got[i] == ref, i
+
+
+def test_decode_capacity_error(lzb, oracle, corpus):
+    b = corpus.generate(10000, 1, 0, 9, 0).tobytes()
+    s = oracle.encode(b, oracle.props(**BASE), alone=True)
+    arr, off, ln = _pack([s])
+    dec = lzb.Decoder()
+    out, out_len, status = dec.code_batch(arr, off, ln, np.zeros(1, dtype=np.uint64), np.array([5000], dtype=np.uint64))
+    assert int(status[0]) == lzb.LZB_E_CAPACITY and int(out_len[0]) <= 5000
+    dec.close()
+
+
+def test_decoder_class_mirrors_reference(lzb, oracle, corpus):
+    """LzmaAlone.java:220-239 written against the mirror classes."""
+    import io
+    b = corpus.generate(100000, 1, 0, 10, 0).tobytes()
+    p = oracle.props(**BASE)
+    s = oracle.encode(b, p, alone=True)
+    dec = lzb.Decoder()
+    assert not dec.SetDecoderProperties(s[:4])
+    assert not dec.SetDecoderProperties(bytes([225, 0, 0, 16, 0]))
+    assert dec.SetDecoderProperties(s[:5])
+    out = io.BytesIO()
+    assert dec.Code(io.BytesIO(s[13:]), out, int.from_bytes(s[5:13], "little"))
+    assert out.getvalue() == b
+    out = io.BytesIO()
+    assert not dec.Code(io.BytesIO(b"\x00" + b"\xff" * 40), out, 1000)
+    dec.close()
+
+
+def test_decode_many_streams(lzb, oracle, corpus):
+    """More streams than resident warp slots (148 SMs x 15): exercises the ticket queue."""
+    n = 3000
+    data = corpus.generate(4096, n, corpus.MIXED, 11)
+    off = np.arange(n, dtype=np.uint64) * 4096
+    ln = np.full(n, 4096, dtype=np.uint64)
+    comp, coff, clen = oracle.encode_batch(data, off, ln, oracle.props(**BASE), with_header=True, threads=8)
+    dec = lzb.Decoder()
+    cap = np.full(n, 4096 + 273, dtype=np.uint64)
+    ooff = np.arange(n, dtype=np.uint64) * (4096 + 273)
+    out, out_len, status = dec.code_batch(comp, coff, clen, ooff, cap)
+    dec.close()
+    assert (status == 1).all() and (out_len == 4096).all()
+    got = out.reshape(n, 4096 + 273)[:, :4096].reshape(-1)
+    assert np.array_equal(got, data)
