@@ -55,4 +55,25 @@ struct MfWave {
     uint32_t* overflow;      // [1]                      zeroed; set when a block ran out of pair slots
 };
 
+struct ParseArgs {
+    MfWave mf;               // inputs + match lists of the wave
+    uint8_t* out;
+    const uint64_t* out_off; // already offset to the wave's first block
+    const uint64_t* out_cap;
+    uint64_t* out_len;
+    uint32_t* ticket;        // zeroed
+    void* opt_scratch;       // [grid * warps][4096] packed _optimum nodes
+    uint16_t* lit_scratch;   // [grid * warps][0x300 << (lc+lp)] when the literal model does not fit shared memory
+    int32_t dict_size, dist_table_size;
+    int32_t lc, lp, pb, fb;
+    bool eos, with_header;
+};
+
+cudaError_t upload_mf_tables();
+cudaError_t launch_mf(const MfWave& w, uint32_t max_len, cudaStream_t st);
+cudaError_t launch_parse(const ParseArgs& a, int grid, int warps, cudaStream_t st);
+size_t parse_smem_bytes(int warps);
+bool parse_lit_in_smem(int lc, int lp, int pb, int fb);
+size_t parse_opt_bytes_per_slot();
+
 }  // namespace lzb

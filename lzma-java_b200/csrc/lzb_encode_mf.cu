@@ -1,0 +1,220 @@
+// lzb_encode_mf.cu -- the bt4 / bt2 binary-tree match finder as a parallel
+// pre-pass (LZ/BinTree.java:152-356 of rfalke/lzma-java).
+//
+// fillMatches0 and Skip update the hash heads and the tree identically, and
+// every position goes through exactly one of them in order, so the list of
+// (length, distance) pairs of a position is a pure function of the data
+// (SURVEY.md section 3.1).  Two kernels reproduce it bit for bit:
+//
+//   link:  the three head tables _hash[h2], _hash[1024+h3], _hash[66560+h4]
+//          are "latest earlier position with the same key".  One warp per
+//          block replays them 32 positions per step: __match_any_sync finds
+//          equal keys inside the step (the nearest lower lane is the
+//          predecessor), the table supplies the predecessor from earlier
+//          steps, and the highest lane of each key group writes the table.
+//          Output: per position its hash-2 / hash-3 candidates and a forward
+//          link to the next position of the same hash-4 bucket.
+//   tree:  distinct hash-4 buckets own disjoint trees (App. C): the descent
+//          for position p starts at the bucket's previous position and only
+//          touches nodes linked by that bucket; p's own two slots are its
+//          own.  One thread per bucket walks the forward links and performs
+//          the reference's insertion for each position, with _son indexed by
+//          absolute position (no cyclic reuse, so buckets never alias;
+//          candidates at or below matchMinPos are cut exactly as in
+//          BinTree.java:164,231).
+#include "lzb_encode.cuh"
+
+namespace lzb {
+
+__constant__ uint32_t c_crc[256];  // CRC.java:6-20, the hash mixer of BinTree.java:171-175
+
+static uint32_t h_crc[256];
+static bool h_crc_ready = false;
+
+cudaError_t upload_mf_tables() {
+    if (!h_crc_ready) {
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t r = i;
+            for (int j = 0; j < 8; j++) r = (r & 1) ? (r >> 1) ^ 0xEDB88320u : r >> 1;
+            h_crc[i] = r;
+        }
+        h_crc_ready = true;
+    }
+    return cudaMemcpyToSymbol(c_crc, h_crc, sizeof h_crc);
+}
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// predecessor of `key` for this lane: nearest lower lane of the same key in
+// this step, else the table entry; the highest lane of the group updates the table.
+__device__ __forceinline__ uint32_t link_step(uint32_t* table, uint32_t key, unsigned vm, int lane, uint32_t base,
+                                              uint32_t pos1) {
+    const unsigned peers = __match_any_sync(vm, key);
+    const unsigned lower = peers & ((1u << lane) - 1u);
+    const uint32_t prev = lower ? base + 32u - (uint32_t)__clz(lower) : table[key];
+    __syncwarp(vm);  // every lane has read the table before the group leaders overwrite it
+    if ((peers >> lane) == 1u) table[key] = pos1;
+    return prev;
+}
+
+__global__ void __launch_bounds__(128) lzb_mf_link_kernel(MfWave w) {
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= w.n_blocks) return;
+    const uint8_t* data = w.in + w.in_off[b];
+    const uint32_t n = (uint32_t)w.in_len[b];
+    uint32_t* heads = w.heads + (size_t)b * w.hash_stride;
+    uint32_t* next = w.next + (size_t)b * w.np;
+    uint32_t* prev2 = w.prev2 + (size_t)b * w.np;
+    uint32_t* prev3 = w.prev3 + (size_t)b * w.np;
+    uint32_t* idx = w.idx + (size_t)b * w.np;
+    uint32_t* head4 = w.bt4 ? heads + kHash2Size + kHash3Size : heads;  // kFixHashSize, BinTree.java:57-69
+    const uint32_t min_check = w.bt4 ? 4 : 3;                           // kMinMatchCheck
+
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t p = base + lane, pos1 = p + 1;
+        const bool in_range = p < n;
+        // positions with lenLimit < kMinMatchCheck are not inserted at all (BinTree.java:158-161)
+        const bool valid = in_range && n - p >= min_check;
+        const unsigned vm = __ballot_sync(kFull, valid);
+        if (valid) {
+            uint32_t h4, c2 = 0, c3 = 0;
+            if (w.bt4) {
+                uint32_t t = c_crc[data[p]] ^ data[p + 1];
+                const uint32_t h2 = t & (kHash2Size - 1);
+                t ^= (uint32_t)data[p + 2] << 8;
+                const uint32_t h3 = t & (kHash3Size - 1);
+                h4 = (t ^ (c_crc[data[p + 3]] << 5)) & w.hash_mask;
+                c2 = link_step(heads, h2, vm, lane, base, pos1);
+                c3 = link_step(heads + kHash2Size, h3, vm, lane, base, pos1);
+            } else {
+                h4 = data[p] ^ ((uint32_t)data[p + 1] << 8);
+            }
+            const uint32_t prev4 = link_step(head4, h4, vm, lane, base, pos1);
+            if (prev4) next[prev4] = pos1;
+            prev2[pos1] = c2 | (prev4 ? 0u : kHeadFlag);
+            prev3[pos1] = c3;
+        } else if (in_range) {
+            idx[pos1] = kMfEmpty;
+            prev2[pos1] = 0;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256) lzb_mf_tree_kernel(MfWave w) {
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = (uint32_t)w.in_len[b];
+    const uint32_t p0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p0 >= n) return;
+    const uint32_t* prev2 = w.prev2 + (size_t)b * w.np;
+    uint32_t pos1 = p0 + 1;
+    if (!(prev2[pos1] & kHeadFlag)) return;  // not the first position of a bucket
+
+    const uint8_t* buf = w.in + w.in_off[b] - 1;  // buf[pos1] is the byte at 1-based position pos1
+    const uint32_t* prev3 = w.prev3 + (size_t)b * w.np;
+    const uint32_t* next = w.next + (size_t)b * w.np;
+    uint32_t* son = w.son + (size_t)b * 2 * w.np;
+    uint32_t* idx = w.idx + (size_t)b * w.np;
+    uint32_t* pairs_out = w.pairs + (size_t)b * w.pair_cap;
+    const uint32_t direct = w.bt4 ? 0 : 2;  // kNumHashDirectBytes
+
+    uint32_t pairs[kMatchMaxLen];
+    uint32_t cur_match = 0;  // the hash-4 head: previous position of this bucket (0 = kEmptyHashValue)
+    while (pos1 != 0) {
+        const uint32_t nxt = next[pos1];
+        const uint32_t remaining = n - (pos1 - 1);
+        const uint32_t len_limit = remaining < (uint32_t)w.fb ? remaining : (uint32_t)w.fb;  // BinTree.java:153-162
+        const uint32_t match_min_pos = pos1 > w.cyclic_size ? pos1 - w.cyclic_size : 0;     // :164
+        const uint8_t* cur = buf + pos1;
+        uint32_t max_len = 1, cnt = 0;  // kStartMaxLen
+        if (w.bt4) {  // :183-208
+            uint32_t c2 = prev2[pos1] & ~kHeadFlag;
+            const uint32_t c3 = prev3[pos1];
+            if (c2 > match_min_pos && buf[c2] == cur[0]) {
+                max_len = 2;
+                pairs[cnt++] = (2u << kPairDistBits) | (pos1 - c2 - 1);
+            }
+            if (c3 > match_min_pos && buf[c3] == cur[0]) {
+                if (c3 == c2) cnt--;
+                max_len = 3;
+                pairs[cnt++] = (3u << kPairDistBits) | (pos1 - c3 - 1);
+                c2 = c3;
+            }
+            if (cnt != 0 && c2 == cur_match) {
+                cnt--;
+                max_len = 1;
+            }
+        } else if (cur_match > match_min_pos && buf[cur_match + 2] != cur[2]) {  // :218-226
+            max_len = 2;
+            pairs[cnt++] = (2u << kPairDistBits) | (pos1 - cur_match - 1);
+        }
+
+        uint32_t ptr0 = 2 * pos1 + 1, ptr1 = 2 * pos1;
+        uint32_t len0 = direct, len1 = direct;
+        int32_t count = w.cut;
+        uint32_t cm = cur_match;
+        for (;;) {  // :230-270
+            if (cm <= match_min_pos || count-- == 0) {
+                son[ptr0] = 0;
+                son[ptr1] = 0;
+                break;
+            }
+            const uint8_t* pby1 = buf + cm;
+            uint32_t len = len0 < len1 ? len0 : len1;
+            if (pby1[len] == cur[len]) {
+                while (++len != len_limit)
+                    if (pby1[len] != cur[len]) break;
+                if (max_len < len) {
+                    max_len = len;
+                    pairs[cnt++] = (len << kPairDistBits) | (pos1 - cm - 1);
+                    if (len == len_limit) {
+                        son[ptr1] = son[2 * cm];
+                        son[ptr0] = son[2 * cm + 1];
+                        break;
+                    }
+                }
+            }
+            if (pby1[len] < cur[len]) {
+                son[ptr1] = cm;
+                ptr1 = 2 * cm + 1;
+                cm = son[ptr1];
+                len1 = len;
+            } else {
+                son[ptr0] = cm;
+                ptr0 = 2 * cm;
+                cm = son[ptr0];
+                len0 = len;
+            }
+        }
+
+        uint32_t where = kMfEmpty;
+        if (cnt) {
+            const uint32_t off = atomicAdd(&w.pair_used[b], cnt + 1);
+            if (off + cnt + 1 <= w.pair_cap) {
+                where = off;
+                pairs_out[off] = cnt;
+                for (uint32_t i = 0; i < cnt; i++) pairs_out[off + 1 + i] = pairs[i];
+            } else {
+                *w.overflow = 1;
+            }
+        }
+        idx[pos1] = where;
+        cur_match = pos1;
+        pos1 = nxt;
+    }
+}
+
+cudaError_t launch_mf(const MfWave& w, uint32_t max_len, cudaStream_t st) {
+    if (w.n_blocks == 0) return cudaSuccess;
+    const uint32_t warps_per_cta = 4;
+    lzb_mf_link_kernel<<<(w.n_blocks + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, st>>>(w);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (max_len == 0) return cudaSuccess;
+    dim3 grid((max_len + 255) / 256, w.n_blocks);
+    lzb_mf_tree_kernel<<<grid, 256, 0, st>>>(w);
+    return cudaGetLastError();
+}
+
+}  // namespace lzb

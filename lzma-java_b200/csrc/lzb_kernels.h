@@ -59,6 +59,9 @@ struct EncScratch {
     void release();
 };
 
+constexpr int kEncMaxWarps = 9;            // parser streams resident per SM
+constexpr size_t kEncSliceBytes = 25088;   // 3 KiB CTA tables + 9 * 25 088 B = 228 864 B <= 227 KB per CTA
+
 // Enqueue the whole encode pipeline for the batch on `st`.
 cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cudaStream_t st, int* launches);
 

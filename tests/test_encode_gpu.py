@@ -1,0 +1,158 @@
+"""GPU parity for the encoder pipeline (BinTree.java:152-356, Encoder.java:275-1125)
+through the C ABI: compressed bytes must be bit-identical to the CPU oracle (which
+reproduces the reference's 12 golden vectors) for every block and property set."""
+import hashlib
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import FIREFOX
+
+pytestmark = pytest.mark.gpu
+
+BASE = dict(dict_size=1 << 20, lc=3, lp=0, pb=2, fb=32, mf=1, eos=False)
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _encoder(lzb, p):
+    enc = lzb.Encoder()
+    assert enc.SetDictionarySize(p["dict_size"])
+    assert enc.SetNumFastBytes(p["fb"])
+    assert enc.SetMatchFinder(p["mf"])
+    assert enc.SetLcLpPb(p["lc"], p["lp"], p["pb"])
+    enc.SetEndMarkerMode(p["eos"])
+    return enc
+
+
+def _gpu_streams(lzb, p, blocks, with_header=True):
+    off = np.zeros(len(blocks), dtype=np.uint64)
+    ln = np.array([len(b) for b in blocks], dtype=np.uint64)
+    if len(blocks) > 1:
+        off[1:] = np.cumsum(ln)[:-1]
+    arr = np.frombuffer(b"".join(blocks), dtype=np.uint8) if ln.sum() else np.zeros(1, dtype=np.uint8)
+    enc = _encoder(lzb, p)
+    out, ooff, olen = enc.code_batch(arr, off, ln, with_header=with_header)
+    enc.close()
+    return [out[int(o): int(o + l)].tobytes() for o, l in zip(ooff, olen)]
+
+
+def _check(lzb, oracle, p, blocks):
+    got = _gpu_streams(lzb, p, blocks)
+    for i, b in enumerate(blocks):
+        ref = oracle.encode(b, oracle.props(**p), alone=True)
+        assert len(got[i]) == len(ref), (i, len(b), len(got[i]), len(ref))
+        assert got[i] == ref, (i, len(b))
+
+
+def test_encode_tiny_and_ragged_blocks(lzb, oracle, corpus):
+    blocks = [b"", b"a", b"ab", b"abc", b"abcd", b"aaaaa", b"abcabcabcabc", b"\x00" * 300, bytes(range(256)) * 2]
+    for cls in range(4):
+        for size in (5, 63, 64, 65, 1000, 4097):
+            blocks.append(corpus.generate(size, 1, cls, 20, size).tobytes())
+    _check(lzb, oracle, BASE, blocks)
+
+
+def test_encode_all_classes_64k(lzb, oracle, corpus):
+    blocks = [corpus.generate(65536, 1, cls, 21, k).tobytes() for cls in range(4) for k in range(3)]
+    _check(lzb, oracle, BASE, blocks)
+
+
+@pytest.mark.parametrize("kw", [{"fb": 5}, {"fb": 64}, {"fb": 128, "dict_size": 1 << 23}, {"fb": 273, "dict_size": 1 << 23},
+                                {"mf": 0}, {"mf": 2}, {"eos": True}, {"lc": 0}, {"lc": 8}, {"lp": 1}, {"lp": 4}, {"pb": 0},
+                                {"pb": 4}, {"pb": 4, "fb": 273}, {"dict_size": 1}, {"dict_size": 4096},
+                                {"dict_size": 100000, "fb": 48}, {"dict_size": 1 << 22}, {"lc": 4, "lp": 4, "pb": 3}])
+def test_encode_property_variants(lzb, oracle, corpus, kw):
+    p = dict(BASE)
+    p.update(kw)
+    blocks = [corpus.generate(40000 + 123 * c, 1, c, 22, 1).tobytes() for c in range(4)]
+    _check(lzb, oracle, p, blocks)
+
+
+def test_encode_degenerate_runs(lzb, oracle):
+    blocks = [b"\x00" * 100000, b"ab" * 50000, b"abc" * 30000, (b"x" * 1000 + b"y") * 90,
+              bytes([i % 251 for i in range(100000)])]
+    _check(lzb, oracle, BASE, blocks)
+    p = dict(BASE)
+    p.update(fb=273, dict_size=1 << 16)
+    _check(lzb, oracle, p, blocks)
+
+
+def test_encode_committed_golden_fixtures(lzb, corpus):
+    """tests/golden/oracle_vectors.json (made by the pinned oracle) against the GPU encoder."""
+    vec = json.load(open(os.path.join(GOLDEN, "oracle_vectors.json")))
+    for c in vec["cases"]:
+        data = corpus.generate(c["size"], 1, c["cls"], c["config_id"], c["block"]).tobytes()
+        s = _gpu_streams(lzb, c["props"], [data])[0]
+        assert len(s) == c["out_len"] and hashlib.sha256(s).hexdigest() == c["out_sha256"], c
+
+
+def test_encode_payload_only_and_class_api(lzb, oracle, corpus):
+    """LzmaAlone.java:190-218 written against the mirror class."""
+    data = corpus.generate(200000, 1, 0, 23, 0).tobytes()
+    p = dict(BASE)
+    p.update(dict_size=1 << 23, fb=128)
+    enc = _encoder(lzb, p)
+    assert not enc.SetNumFastBytes(4) and not enc.SetNumFastBytes(274)
+    assert not enc.SetDictionarySize(0) and not enc.SetDictionarySize((1 << 29) + 1)
+    assert not enc.SetLcLpPb(9, 0, 0) and not enc.SetLcLpPb(0, 5, 0) and not enc.SetLcLpPb(0, 0, 5)
+    assert not enc.SetMatchFinder(3) and lzb.Encoder.SetAlgorithm(2)
+    out = io.BytesIO()
+    enc.WriteCoderProperties(out)
+    assert out.getvalue() == oracle.props_bytes(oracle.props(**p))
+
+    class Progress:
+        calls = []
+
+        def SetProgress(self, a, b):
+            self.calls.append((a, b))
+
+    pr = Progress()
+    payload = io.BytesIO()
+    enc.Code(io.BytesIO(data), payload, -1, -1, pr)
+    enc.close()
+    assert payload.getvalue() == oracle.encode(data, oracle.props(**p))
+    assert pr.calls and pr.calls[-1][0] >= len(data)  # LzmaBench.java:219-223,366-368
+
+
+def test_encode_1mib_blocks_c3(lzb, oracle, corpus):
+    """BASELINE config 3 shape: 1 MiB blocks, dict 1 MiB, fb 64, mixed corpus (8 blocks here)."""
+    p = dict(BASE)
+    p.update(fb=64)
+    n, size = 8, 1 << 20
+    data = corpus.generate(size, n, corpus.MIXED, 3)
+    off = np.arange(n, dtype=np.uint64) * size
+    ln = np.full(n, size, dtype=np.uint64)
+    ref, roff, rlen = oracle.encode_batch(data, off, ln, oracle.props(**p), True, 8)
+    enc = _encoder(lzb, p)
+    out, ooff, olen = enc.code_batch(data, off, ln, with_header=True)
+    enc.close()
+    assert np.array_equal(olen, rlen)
+    for i in range(n):
+        assert np.array_equal(out[int(ooff[i]): int(ooff[i] + olen[i])], ref[int(roff[i]): int(roff[i] + rlen[i])]), i
+
+
+@pytest.mark.skipif(not os.path.exists(FIREFOX), reason="reference fixture only exists in the build container")
+def test_encode_firefox_golden_md5(lzb):
+    data = open(FIREFOX, "rb").read()
+    s = lzb.encode_alone(data)
+    assert len(s) == 138940 and hashlib.md5(s).hexdigest() == "93c6983fcfa73e55099a11ee13139687"
+
+
+def test_roundtrip_gpu_encode_gpu_decode(lzb, corpus):
+    n, size = 64, 100000
+    data = corpus.generate(size, n, corpus.MIXED, 24)
+    off = np.arange(n, dtype=np.uint64) * size
+    ln = np.full(n, size, dtype=np.uint64)
+    enc = _encoder(lzb, BASE)
+    out, ooff, olen = enc.code_batch(data, off, ln, with_header=True)
+    enc.close()
+    dec = lzb.Decoder()
+    cap = np.full(n, size + 273, dtype=np.uint64)
+    doff = np.arange(n, dtype=np.uint64) * (size + 273)
+    dout, dlen, status = dec.code_batch(out, ooff, olen, doff, cap)
+    dec.close()
+    assert (status == 1).all() and (dlen == size).all()
+    assert np.array_equal(dout.reshape(n, size + 273)[:, :size].reshape(-1), data)
