@@ -4,6 +4,7 @@
 // independent blocks.  Per wave of blocks:  memset(heads, next, counters) ->
 // lzb_mf_link_kernel -> lzb_mf_tree_kernel -> lzb_parse_kernel.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "lzb_encode.cuh"
@@ -100,9 +101,9 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
     while ((uint32_t)a.dict_size > (1u << dic_log)) dic_log++;  // Encoder.java:1141-1144
 
     // resident parser slots: one CTA per SM, up to kEncMaxWarps streams each
-    const size_t slots = (size_t)num_sms * kEncMaxWarps;
-    const bool lit_smem = parse_lit_in_smem(a.lc, a.lp, a.pb, a.fb);
-    const size_t lit_slots = lit_smem ? 0 : slots * ((size_t)0x300 << (a.lc + a.lp));
+    const ParseGeometry geo = parse_geometry(a.lc, a.lp, a.pb, a.fb);
+    const size_t slots = (size_t)num_sms * geo.max_warps;
+    const size_t lit_slots = geo.lit_in_smem ? 0 : slots * ((size_t)0x300 << (a.lc + a.lp));
 
     size_t free_b = 0, total_b = 0;
     e = cudaMemGetInfo(&free_b, &total_b);
@@ -180,7 +181,10 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
         pa.eos = a.eos;
         pa.with_header = a.with_header;
         int warps = (int)((wb + (uint32_t)num_sms - 1) / (uint32_t)num_sms);
-        warps = std::min(std::max(warps, 1), kEncMaxWarps);
+        warps = std::min(std::max(warps, 1), geo.max_warps);
+        if (const char* ev = getenv("LZB_ENC_WARPS")) warps = std::min(std::max(atoi(ev), 1), geo.max_warps);  // tuning knob
+        pa.slice_bytes = geo.slice_bytes;
+        pa.slice_budget = geo.slice_budget;
         int grid = (int)std::min<uint32_t>((wb + (uint32_t)warps - 1) / (uint32_t)warps, (uint32_t)num_sms);
         e = launch_parse(pa, grid, warps, st);
         if (e != cudaSuccess) return e;

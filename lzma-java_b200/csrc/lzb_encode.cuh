@@ -67,13 +67,20 @@ struct ParseArgs {
     int32_t dict_size, dist_table_size;
     int32_t lc, lp, pb, fb;
     bool eos, with_header;
+    uint32_t slice_bytes;    // shared memory per warp
+    uint32_t slice_budget;   // literal coders stay in shared memory while the slice fits this budget
+};
+
+struct ParseGeometry {
+    uint32_t slice_bytes, slice_budget, cta_table_bytes;
+    int max_warps;           // streams resident per SM
+    bool lit_in_smem;
 };
 
 cudaError_t upload_mf_tables();
 cudaError_t launch_mf(const MfWave& w, uint32_t max_len, cudaStream_t st);
 cudaError_t launch_parse(const ParseArgs& a, int grid, int warps, cudaStream_t st);
-size_t parse_smem_bytes(int warps);
-bool parse_lit_in_smem(int lc, int lp, int pb, int fb);
+ParseGeometry parse_geometry(int lc, int lp, int pb, int fb);
 size_t parse_opt_bytes_per_slot();
 
 }  // namespace lzb

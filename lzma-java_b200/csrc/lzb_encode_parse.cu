@@ -1,29 +1,43 @@
 // lzb_encode_parse.cu -- optimal parse + price tables + range encoder, one
-// warp per block (LZMA/Encoder.java:275-1125, LenEncoder.java,
-// LenPriceTableEncoder.java, LiteralEncoder.java, RangeCoder/RangeEncoder.java,
-// BitTreeEncoder.java, ProbPrices.java of rfalke/lzma-java).
+// warp per block, warp-cooperative (LZMA/Encoder.java:275-1125,
+// LenEncoder.java, LenPriceTableEncoder.java, LiteralEncoder.java,
+// RangeCoder/RangeEncoder.java, BitTreeEncoder.java, ProbPrices.java of
+// rfalke/lzma-java).
 //
 // The match finder has already run (lzb_encode_mf.cu): ReadMatchDistances
 // reads the position's list from global memory and Skip is a cursor bump.
 // What remains is the strictly serial chain  parse chunk -> emit chunk ->
-// parse next chunk with the adapted probabilities  (SURVEY.md section 3.1),
-// kept per warp with the whole model and every price table in the warp's
-// private slice of shared memory:
-//   probabilities  pb-strided layout of lzb_common.cuh (7 320 u16 at lc3 lp0 pb2)
-//   prices         u16 tables (a price never exceeds 10 * 576)
-//   match list     the current position's pairs (the parser truncates them in
-//                  place, Encoder.java:737-743)
-//   _optimum[]     32-byte packed nodes in global memory (L1/L2 resident)
-// Every relaxation keeps the reference's order and comparison (strict <, one
-// <= for the short rep, App. A #8) so ties resolve identically.
+// parse next chunk with the adapted probabilities  (SURVEY.md section 3.1).
+// Within that chain the warp works as one:
+//   * every lane holds the same copy of the scalar parser state (state, reps,
+//     cursor, prices of the current node), so control flow is uniform;
+//   * byte comparisons (InWindow.GetMatchLen) are done 32 bytes per step:
+//     each lane loads one byte of the window and one byte per rep distance,
+//     a ballot gives the equality bitmap, and both the rep length and the
+//     "literal + rep0" continuation (Encoder.java:640,698,769) are run
+//     lengths in that bitmap;
+//   * the relaxation loops over lengths (Encoder.java:463-473, 484-500,
+//     675-688, 755-808) give one length to each lane; candidates that can
+//     reach the same node are applied in the reference's order with the
+//     reference's comparison (strict <, one <= for the short rep), so ties
+//     resolve identically (App. A #8);
+//   * literal prices use eight lanes, one per bit; price-table refreshes use
+//     one lane per table entry;
+//   * emission (the adaptive range coder) is a serial chain and runs on lane 0.
+// Shared memory per warp: the probability model (pb-strided layout), all
+// price tables as u16, the current match list, and a ring of R = 2^k >= 4 fb + 3
+// packed 32-byte _optimum nodes.  A parse chunk may span 4095 positions, but a
+// step only touches nodes [cur - 2fb - 1, cur + 2fb + 1]; older nodes are
+// written back to global memory and Backward runs there when a chunk wrapped.
 #include "lzb_encode.cuh"
 
 namespace lzb {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr int kNumOpts = 1 << 12;           // Encoder.java:19
+constexpr int kNumOpts = 1 << 12;               // Encoder.java:19
 constexpr uint32_t kInfinityPrice = 0xFFFFFFF;  // Encoder.java:22
-constexpr int kNumBitPriceShiftBits = 6;    // ProbPrices.java:6
+constexpr int kNumBitPriceShiftBits = 6;        // ProbPrices.java:6
+constexpr uint32_t kLit = 0xFFFFFFFFu;          // back value of a literal ("-1")
 
 // ---- tables shared by the CTA ----------------------------------------------
 struct CtaTables {
@@ -42,7 +56,6 @@ __device__ void init_cta_tables(CtaTables* t) {
         t->prob_prices[j] = (uint16_t)v;
     }
     for (int c = threadIdx.x; c < 2048; c += blockDim.x) {
-        // slot s >= 2 covers k = 2^((s>>1)-1) consecutive values starting at c0(s)
         uint32_t s;
         if (c < 2) {
             s = (uint32_t)c;
@@ -58,7 +71,7 @@ __device__ void init_cta_tables(CtaTables* t) {
 // ---- packed _optimum node (Optimal.java:4-33) ------------------------------
 struct __align__(16) OptNode {
     uint32_t price;
-    uint32_t back_prev;   // 0xFFFFFFFF = literal ("-1")
+    uint32_t back_prev;   // kLit = literal
     uint32_t back_prev2;
     uint32_t link;        // pos_prev | pos_prev2 << 12 | state << 24 | prev1_is_char << 28 | prev2 << 29
     uint32_t backs[4];
@@ -72,7 +85,7 @@ __device__ __forceinline__ int ln_state(uint32_t l) { return (int)((l >> 24) & 0
 __device__ __forceinline__ bool ln_prev1(uint32_t l) { return (l >> 28) & 1; }
 __device__ __forceinline__ bool ln_prev2(uint32_t l) { return (l >> 29) & 1; }
 
-// ---- range encoder (RangeEncoder.java:23-87) -------------------------------
+// ---- range encoder (RangeEncoder.java:23-87); lives in lane 0 ---------------
 struct RangeEnc {
     uint64_t low;
     uint32_t range;
@@ -157,9 +170,40 @@ struct RangeEnc {
     }
 };
 
-// ---- everything one stream needs -------------------------------------------
+// ---- shared-memory slice of one warp ----------------------------------------
+struct SliceLayout {
+    uint32_t dist_prices, slot_prices, align_prices, len_prices, len_counters, md, md2, ring, total;  // byte offsets
+    uint32_t ring_nodes;
+    bool lit_in_smem;
+};
+__host__ __device__ inline SliceLayout make_slice(int lc, int lp, int pb, int fb, uint32_t budget) {
+    const ModelLayout L = make_layout(lc, lp, pb);
+    const uint32_t table = (uint32_t)(fb - 1);
+    uint32_t ring_nodes = 256;
+    while (ring_nodes < (uint32_t)(4 * fb + 3)) ring_nodes <<= 1;
+    SliceLayout s;
+    for (int with_lit = 1; with_lit >= 0; with_lit--) {
+        uint32_t o = (uint32_t)(L.n_fixed + (with_lit ? L.n_literal : 0)) * 2;
+        o = (o + 15) & ~15u;
+        s.dist_prices = o;  o += 512 * 2;
+        s.slot_prices = o;  o += 256 * 2;
+        s.align_prices = o; o += 16 * 2;
+        s.len_prices = o;   o += ((2u << pb) * table * 2 + 15) & ~15u;
+        s.len_counters = o; o += 32 * 4;
+        s.md = o;           o += 288 * 4;
+        s.md2 = o;          o += 288 * 2;
+        o = (o + 15) & ~15u;
+        s.ring = o;         o += ring_nodes * 32;
+        s.total = o;
+        s.ring_nodes = ring_nodes;
+        s.lit_in_smem = with_lit != 0;
+        if (s.total <= budget || !with_lit) break;
+    }
+    return s;
+}
+
+// ---- everything one stream needs (identical in every lane unless noted) -----
 struct Enc {
-    // tables / shared memory
     const CtaTables* T;
     uint16_t* model;        // fixed part of the probability model (shared)
     uint16_t* lit;          // literal coders (shared, or global when they do not fit)
@@ -169,25 +213,26 @@ struct Enc {
     uint16_t* len_prices;   // [2][1<<pb][table_size]
     int32_t* len_counters;  // [2][16]
     uint32_t* md;           // current match list, len << 23 | distance
-    OptNode* opt;           // [kNumOpts]
+    uint16_t* md2;          // per pair: length of the rep0 continuation after "match + literal"
+    OptNode* ring;          // [R] shared
+    OptNode* gopt;          // [kNumOpts] global spill
+    OptNode* qbase;         // where Backward left the decision queue (ring or gopt)
+    uint32_t rmask;
     ModelLayout L;
-    // stream
     const uint8_t* data;
     uint32_t n;
     const uint32_t* idx;    // 1-based
     const uint32_t* pairs;
-    // parameters
+    int lane;
     int lc, lp, pb, fb, table_size, dist_table_size;
     uint32_t pos_mask, lp_mask;
     bool eos;
-    // state (Encoder.java:132-181)
-    RangeEnc rc;
+    RangeEnc rc;            // meaningful in lane 0 only
     uint32_t m;             // match-finder cursor, 0-based (== _pos - 1 of the reference's InWindow)
+    uint32_t pre_pos, pre_off;  // prefetched idx[] entry
     int state;
     uint32_t prev_byte;
     uint32_t rep_dist[4];
-    uint32_t reps[4];
-    uint32_t rep_lens[4];
     int num_pairs;
     int additional_offset;
     int opt_end, opt_cur;
@@ -244,17 +289,43 @@ struct Enc {
         return lit + 0x300u * (((pos & lp_mask) << lc) + (prev >> (8 - lc)));
     }
 
+    __device__ __forceinline__ OptNode* node(int i) const { return ring + ((uint32_t)i & rmask); }
+
     // ---- window (InWindow.java:115-138, whole block resident) ----
     __device__ __forceinline__ uint32_t byte_at(int index) const { return data[m + index]; }
     __device__ __forceinline__ int avail() const { return (int)(n - m); }
-    __device__ int match_len(int index, uint32_t distance, int limit) const {
-        const uint32_t s = m + index;
-        if (s + limit > n) limit = (int)(n - s);
+
+    // GetMatchLen for an absolute start `s`, 32 bytes per round (all lanes, uniform result)
+    __device__ int match_len_abs(uint32_t s, uint32_t distance, int limit) const {
+        if (limit > 0 && s + (uint32_t)limit > n) limit = (int)(n - s);
         const uint8_t* a = data + s;
         const uint8_t* b = a - distance - 1;
-        int i = 0;
-        while (i < limit && a[i] == b[i]) i++;
-        return i;
+        int len = 0;
+        while (len < limit) {
+            const int i = len + lane;
+            const bool ok = i < limit;
+            uint32_t x = 0, y = 1;
+            if (ok) {
+                x = a[i];
+                y = b[i];
+            }
+            const unsigned neq = __ballot_sync(kFull, x != y);
+            if (neq) return len + (__ffs(neq) - 1);
+            len += 32;
+        }
+        return limit > 0 ? limit : 0;
+    }
+
+    // run of set bits in a 32-byte equality bitmap starting at bit `start`, continued in memory
+    // when it runs off the bitmap; `base` is the absolute position of bit 0, capped at `limit`
+    __device__ __forceinline__ int eq_run(unsigned e, int start, uint32_t base, uint32_t distance, int limit) const {
+        if (limit <= 0) return 0;
+        if (start >= 32) return match_len_abs(base + start, distance, limit);
+        const int room = 32 - start;
+        const unsigned w = ~(e >> start);
+        const int run = w ? __ffs(w) - 1 : 32;  // for start > 0 the top `start` bits of w are set, so run <= room
+        if (run >= room && limit > room) return room + match_len_abs(base + 32, distance, limit - room);
+        return run < limit ? run : limit;
     }
 
     // ---- match list ----
@@ -262,18 +333,24 @@ struct Enc {
     __device__ __forceinline__ uint32_t md_dist(int i) const { return md[i] & kPairDistMask; }
 
     __device__ int read_match_distances() {  // Encoder.java:275-287
-        const uint32_t off = idx[m + 1];
+        __syncwarp();  // everyone is done with the previous list
+        const uint32_t off = (pre_pos == m + 1) ? pre_off : idx[m + 1];
         int cnt = 0;
         if (off != kMfEmpty) {
             cnt = (int)pairs[off];
-            for (int i = 0; i < cnt; i++) md[i] = pairs[off + 1 + i];
+            for (int i = lane; i < cnt; i += 32) md[i] = pairs[off + 1 + i];
         }
+        __syncwarp();
         num_pairs = cnt;
         m++;  // fillMatches advanced the window
+        if (m < n) {  // prefetch the next position's list head
+            pre_pos = m + 1;
+            pre_off = idx[m + 1];
+        }
         int length = 0;
         if (cnt > 0) {
             length = md_len(cnt - 1);
-            if (length == fb) length += match_len(length - 1, md_dist(cnt - 1), kMatchMaxLen - length);
+            if (length == fb) length += match_len_abs(m + length - 1, md_dist(cnt - 1), kMatchMaxLen - length);
         }
         additional_offset++;
         return length;
@@ -289,20 +366,25 @@ struct Enc {
     __device__ __forceinline__ uint32_t len_price(int which, int symbol, uint32_t ps) const {
         return len_prices[((which << pb) + ps) * table_size + symbol];
     }
-    __device__ void len_update_table(int which, uint32_t ps) {  // LenEncoder.SetPrices :50-71 + UpdateTable :20-23
+    // LenEncoder.SetPrices :50-71 + UpdateTable :20-23, one lane per symbol
+    __device__ void len_update_table(int which, uint32_t ps) {
+        __syncwarp();
         const uint16_t* lp_ = model + (which ? L.rep_len : L.len);
         uint16_t* prices = len_prices + ((which << pb) + ps) * table_size;
         const uint32_t a0 = price0(lp_[0]), a1 = price1(lp_[0]);
         const uint32_t b0 = a1 + price0(lp_[1]), b1 = a1 + price1(lp_[1]);
-        int i = 0;
-        for (; i < kNumLowLenSymbols && i < table_size; i++) prices[i] = (uint16_t)(a0 + tree_price(lp_ + len_low(pb, ps), kNumLowLenBits, i));
-        for (; i < kNumLowLenSymbols + kNumMidLenSymbols && i < table_size; i++)
-            prices[i] = (uint16_t)(b0 + tree_price(lp_ + len_mid(pb, ps), kNumMidLenBits, i - kNumLowLenSymbols));
-        for (; i < table_size; i++)
-            prices[i] = (uint16_t)(b1 + tree_price(lp_ + len_high(pb), kNumHighLenBits, i - kNumLowLenSymbols - kNumMidLenSymbols));
-        len_counters[which * 16 + ps] = table_size;
+        for (int i = lane; i < table_size; i += 32) {
+            uint32_t v;
+            if (i < kNumLowLenSymbols) v = a0 + tree_price(lp_ + len_low(pb, ps), kNumLowLenBits, i);
+            else if (i < kNumLowLenSymbols + kNumMidLenSymbols) v = b0 + tree_price(lp_ + len_mid(pb, ps), kNumMidLenBits, i - kNumLowLenSymbols);
+            else v = b1 + tree_price(lp_ + len_high(pb), kNumHighLenBits, i - kNumLowLenSymbols - kNumMidLenSymbols);
+            prices[i] = (uint16_t)v;
+        }
+        if (lane == 0) len_counters[which * 16 + ps] = table_size;
+        __syncwarp();
     }
-    __device__ void len_encode(int which, uint32_t symbol, uint32_t ps) {  // LenEncoder.encode :33-48 + LenPriceTableEncoder.encode :32-37
+    // lane 0: LenEncoder.encode :33-48
+    __device__ void len_encode_bits(int which, uint32_t symbol, uint32_t ps) {
         uint16_t* lp_ = model + (which ? L.rep_len : L.len);
         if (symbol < kNumLowLenSymbols) {
             rc.encode(lp_ + 0, 0);
@@ -317,11 +399,21 @@ struct Enc {
                 rc.tree(lp_ + len_high(pb), kNumHighLenBits, symbol - kNumLowLenSymbols - kNumMidLenSymbols);
             }
         }
-        if (--len_counters[which * 16 + ps] == 0) len_update_table(which, ps);
+    }
+    // all lanes, after the bits were emitted: LenPriceTableEncoder.encode :32-37
+    __device__ void len_count(int which, uint32_t ps) {
+        const int c = len_counters[which * 16 + ps] - 1;
+        __syncwarp();
+        if (c == 0) {
+            len_update_table(which, ps);
+        } else {
+            if (lane == 0) len_counters[which * 16 + ps] = c;
+            __syncwarp();
+        }
     }
 
     // ---- literal coder (LiteralEncoder.java:17-64) ----
-    __device__ void lit_encode(uint16_t* probs, uint32_t symbol) {
+    __device__ void lit_encode(uint16_t* probs, uint32_t symbol) {  // lane 0
         uint32_t context = 1;
         for (int i = 7; i >= 0; i--) {
             const uint32_t bit = (symbol >> i) & 1;
@@ -329,7 +421,7 @@ struct Enc {
             context = (context << 1) | bit;
         }
     }
-    __device__ void lit_encode_matched(uint16_t* probs, uint32_t match_byte, uint32_t symbol) {
+    __device__ void lit_encode_matched(uint16_t* probs, uint32_t match_byte, uint32_t symbol) {  // lane 0
         uint32_t context = 1;
         bool same = true;
         for (int i = 7; i >= 0; i--) {
@@ -344,27 +436,22 @@ struct Enc {
             context = (context << 1) | bit;
         }
     }
+    // Encoder2.GetPrice (:42-64): lanes 0..7 price one bit each; bit i uses the matched
+    // context while every higher bit of symbol and match_byte agrees.  Uniform result.
     __device__ uint32_t lit_price(const uint16_t* probs, bool match_mode, uint32_t match_byte, uint32_t symbol) const {
-        uint32_t price = 0, context = 1;
-        int i = 7;
-        if (match_mode) {
-            for (; i >= 0; i--) {
-                const uint32_t match_bit = (match_byte >> i) & 1;
-                const uint32_t bit = (symbol >> i) & 1;
-                price += price_bit(probs[((1 + match_bit) << 8) + context], bit);
-                context = (context << 1) | bit;
-                if (match_bit != bit) {
-                    i--;
-                    break;
-                }
-            }
-        }
-        for (; i >= 0; i--) {
+        uint32_t price = 0;
+        if (lane < 8) {
+            const int i = 7 - lane;
+            const uint32_t ctx = (0x100u | symbol) >> (i + 1);
             const uint32_t bit = (symbol >> i) & 1;
-            price += price_bit(probs[context], bit);
-            context = (context << 1) | bit;
+            uint32_t index = ctx;
+            if (match_mode && (((match_byte ^ symbol) & 0xFF) >> (i + 1)) == 0) index += (1 + ((match_byte >> i) & 1)) << 8;
+            price = price_bit(probs[index], bit);
         }
-        return price;
+        price += __shfl_xor_sync(kFull, price, 1);
+        price += __shfl_xor_sync(kFull, price, 2);
+        price += __shfl_xor_sync(kFull, price, 4);
+        return __shfl_sync(kFull, price, 0);
     }
 
     // ---- rep / match prices (Encoder.java:296-333) ----
@@ -400,89 +487,124 @@ struct Enc {
         return price + len_price(0, len - kMatchMinLen, ps);
     }
 
-    // ---- price table refresh (Encoder.java:1087-1125) ----
+    // ---- price table refresh (Encoder.java:1087-1125), one lane per entry ----
     __device__ void fill_distances_prices() {
-        uint32_t temp[kNumFullDistances];
-        for (int i = kStartPosModelIndex; i < kNumFullDistances; i++) {
-            const int slot = pos_slot(i);
-            const int footer = (slot >> 1) - 1;
-            const int base = (2 | (slot & 1)) << footer;
-            temp[i] = reverse_price(model + L.pos_dec + base - slot - 1, footer, i - base);
+        __syncwarp();
+        // slot prices first (they do not depend on tempPrices)
+        for (int k = lane; k < kNumLenToPosStates * dist_table_size; k += 32) {
+            const int lps = k / dist_table_size, slot = k - lps * dist_table_size;
+            uint32_t v = tree_price(model + L.pos_slot + (lps << kNumPosSlotBits), kNumPosSlotBits, slot);
+            if (slot >= kEndPosModelIndex) v += (uint32_t)((((slot >> 1) - 1) - kNumAlignBits) << kNumBitPriceShiftBits);
+            slot_prices[(lps << kNumPosSlotBits) + slot] = (uint16_t)v;
         }
-        for (int lps = 0; lps < kNumLenToPosStates; lps++) {
-            const uint16_t* enc = model + L.pos_slot + (lps << kNumPosSlotBits);
-            const int st = lps << kNumPosSlotBits;
-            int slot;
-            for (slot = 0; slot < dist_table_size; slot++) slot_prices[st + slot] = (uint16_t)tree_price(enc, kNumPosSlotBits, slot);
-            for (slot = kEndPosModelIndex; slot < dist_table_size; slot++)
-                slot_prices[st + slot] += (uint16_t)((((slot >> 1) - 1) - kNumAlignBits) << kNumBitPriceShiftBits);
-            const int st2 = lps * kNumFullDistances;
-            int i;
-            for (i = 0; i < kStartPosModelIndex; i++) dist_prices[st2 + i] = slot_prices[st + i];
-            for (; i < kNumFullDistances; i++) dist_prices[st2 + i] = (uint16_t)(slot_prices[st + pos_slot(i)] + temp[i]);
+        __syncwarp();
+        for (int k = lane; k < kNumLenToPosStates * kNumFullDistances; k += 32) {
+            const int lps = k >> 7, i = k & (kNumFullDistances - 1);
+            uint32_t v;
+            if (i < kStartPosModelIndex) {
+                v = slot_prices[(lps << kNumPosSlotBits) + i];
+            } else {
+                const int slot = pos_slot(i);
+                const int footer = (slot >> 1) - 1;
+                const int base = (2 | (slot & 1)) << footer;
+                v = (uint32_t)slot_prices[(lps << kNumPosSlotBits) + slot] + reverse_price(model + L.pos_dec + base - slot - 1, footer, i - base);
+            }
+            dist_prices[lps * kNumFullDistances + i] = (uint16_t)v;
         }
+        __syncwarp();
         match_price_count = 0;
     }
     __device__ void fill_align_prices() {
-        for (int i = 0; i < kAlignTableSize; i++) align_prices[i] = (uint16_t)reverse_price(model + L.pos_align, kNumAlignBits, i);
+        __syncwarp();
+        if (lane < kAlignTableSize) align_prices[lane] = (uint16_t)reverse_price(model + L.pos_align, kNumAlignBits, lane);
+        __syncwarp();
         align_price_count = 0;
     }
 
-    // ---- Backward (Encoder.java:335-362): returns back in *back_out, length as result ----
-    __device__ int backward(int cur, uint32_t* back_out) {
+    // ---- node ring management ----
+    // make nodes (len_end, need] usable: spill the nodes their slots still hold, then price = infinity
+    __device__ void extend(int& len_end, int& wb, int need) {
+        if (need <= len_end) return;
+        const int new_wb = need - (int)rmask;  // need - R + 1
+        if (new_wb > wb) {
+            __syncwarp();
+            const uint4* src = reinterpret_cast<const uint4*>(ring);
+            uint4* dst = reinterpret_cast<uint4*>(gopt);
+            for (int k = 2 * wb + lane; k < 2 * new_wb; k += 32) dst[k] = src[(uint32_t)k & (2 * rmask + 1)];
+            wb = new_wb;
+            __syncwarp();
+        }
+        for (int t = len_end + 1 + lane; t <= need; t += 32) node(t)->price = kInfinityPrice;
+        len_end = need;
+    }
+
+    // strict '<' keeps the first candidate on ties (App. A #8); called by the lane that owns node `at`
+    __device__ __forceinline__ void relax(int at, uint32_t price, uint32_t pos_prev, uint32_t back, bool p1, bool p2,
+                                          uint32_t pos_prev2, uint32_t back2) {
+        OptNode* o = node(at);
+        if (price < o->price) *reinterpret_cast<uint4*>(o) = make_uint4(price, back, back2, mk_link(pos_prev, pos_prev2, p1, p2));
+    }
+
+    // Backward (Encoder.java:335-362).  Runs on lane 0 over `base` (ring when the chunk never
+    // wrapped, else the global spill area after the live part of the ring has been flushed).
+    __device__ int backward(int cur, int wb, uint32_t* back_out) {
+        __syncwarp();
+        OptNode* base = ring;
+        if (wb > 0) {
+            const uint4* src = reinterpret_cast<const uint4*>(ring);
+            uint4* dst = reinterpret_cast<uint4*>(gopt);
+            for (int k = 2 * wb + lane; k < 2 * (cur + 1); k += 32) dst[k] = src[(uint32_t)k & (2 * rmask + 1)];
+            base = gopt;
+            __syncwarp();
+        }
+        qbase = base;
         opt_end = cur;
-        uint32_t pos_mem = ln_pos_prev(opt[cur].link);
-        uint32_t back_mem = opt[cur].back_prev;
-        do {
-            const uint32_t lk = opt[cur].link;
-            if (ln_prev1(lk)) {
-                // MakeAsChar + PosPrev = posMem - 1
-                opt[pos_mem].back_prev = 0xFFFFFFFFu;
-                opt[pos_mem].link = mk_link(pos_mem - 1, 0, false, false);
-                if (ln_prev2(lk)) {
-                    opt[pos_mem - 1].link = mk_link(ln_pos_prev2(lk), 0, false, false);
-                    opt[pos_mem - 1].back_prev = opt[cur].back_prev2;
+        uint32_t res_back = 0, res_cur = 0;
+        if (lane == 0) {
+            OptNode* opt = base;
+            uint32_t pos_mem = ln_pos_prev(opt[cur].link);
+            uint32_t back_mem = opt[cur].back_prev;
+            do {
+                const uint32_t lk = opt[cur].link;
+                if (ln_prev1(lk)) {
+                    opt[pos_mem].back_prev = kLit;  // MakeAsChar + PosPrev = posMem - 1
+                    opt[pos_mem].link = mk_link(pos_mem - 1, 0, false, false);
+                    if (ln_prev2(lk)) {
+                        opt[pos_mem - 1].link = mk_link(ln_pos_prev2(lk), 0, false, false);
+                        opt[pos_mem - 1].back_prev = opt[cur].back_prev2;
+                    }
                 }
-            }
-            const uint32_t pos_prev = pos_mem;
-            const uint32_t back_cur = back_mem;
-            back_mem = opt[pos_prev].back_prev;
-            pos_mem = ln_pos_prev(opt[pos_prev].link);
-            opt[pos_prev].back_prev = back_cur;
-            opt[pos_prev].link = (opt[pos_prev].link & ~0xFFFu) | (uint32_t)cur;  // only PosPrev changes; Prev1IsChar/Prev2 are read next round
-            cur = (int)pos_prev;
-        } while (cur > 0);
-        opt_cur = (int)ln_pos_prev(opt[0].link);
-        *back_out = opt[0].back_prev;
+                const uint32_t pos_prev = pos_mem;
+                const uint32_t back_cur = back_mem;
+                back_mem = opt[pos_prev].back_prev;
+                pos_mem = ln_pos_prev(opt[pos_prev].link);
+                opt[pos_prev].back_prev = back_cur;
+                opt[pos_prev].link = (opt[pos_prev].link & ~0xFFFu) | (uint32_t)cur;  // only PosPrev changes
+                cur = (int)pos_prev;
+            } while (cur > 0);
+            res_cur = ln_pos_prev(opt[0].link);
+            res_back = opt[0].back_prev;
+        }
+        __syncwarp();
+        opt_cur = (int)__shfl_sync(kFull, res_cur, 0);
+        *back_out = __shfl_sync(kFull, res_back, 0);
         return opt_cur;
     }
 
-    // relaxation helper: strict '<' keeps the first candidate on ties (App. A #8)
-    __device__ __forceinline__ void relax(int at, uint32_t price, uint32_t pos_prev, uint32_t back, bool p1, bool p2,
-                                          uint32_t pos_prev2, uint32_t back2) {
-        OptNode* o = &opt[at];
-        if (price < o->price) {
-            o->price = price;
-            o->back_prev = back;
-            o->back_prev2 = back2;
-            o->link = mk_link(pos_prev, pos_prev2, p1, p2);
-        }
-    }
-
     __device__ int get_optimum(uint32_t position, uint32_t* back_out);
-    __device__ void write_end_marker(uint32_t ps);
     __device__ void flush_stream(uint32_t now);
     __device__ bool encode_one();
     __device__ void run();
 };
 
 // getOptimum (Encoder.java:364-811).  Returns the length, *back_out = "pos" of PosAndLength
-// (0xFFFFFFFF literal, 0..3 rep index, else distance + 4).
+// (kLit literal, 0..3 rep index, else distance + 4).  Uniform across the warp.
 __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
     if (opt_end != opt_cur) {  // :365-370
-        const uint32_t lk = opt[opt_cur].link;
+        const OptNode* q = qbase + opt_cur;
+        const uint32_t lk = q->link;
         const int len_res = (int)ln_pos_prev(lk) - opt_cur;
-        *back_out = opt[opt_cur].back_prev;
+        *back_out = q->back_prev;
         opt_cur = (int)ln_pos_prev(lk);
         return len_res;
     }
@@ -500,17 +622,32 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
 
     int num_avail = avail() + 1;
     if (num_avail < 2) {
-        *back_out = 0xFFFFFFFFu;
+        *back_out = kLit;
         return 1;
     }
     if (num_avail > kMatchMaxLen) num_avail = kMatchMaxLen;
 
-    int rep_max_index = 0;
-    for (int i = 0; i < kNumRepDistances; i++) {  // :393-399
+    // window bytes and the four rep comparisons, 32 bytes at once (:393-399, limit 273)
+    uint32_t c = m - 1;  // position of the current byte
+    uint32_t reps[4], rep_lens[4];
+    uint32_t a_byte = 0, b_byte[4] = {1, 1, 1, 1};
+    const bool in_range = c + lane < n;
+    if (in_range) a_byte = data[c + lane];
+    unsigned eq[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
         reps[i] = rep_dist[i];
-        rep_lens[i] = (uint32_t)match_len(-1, reps[i], kMatchMaxLen);
-        if (rep_lens[i] > rep_lens[rep_max_index]) rep_max_index = i;
+        if (in_range) b_byte[i] = data[c + lane - reps[i] - 1];
     }
+    int rep_max_index = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        eq[i] = __ballot_sync(kFull, in_range && a_byte == b_byte[i]);
+        rep_lens[i] = (uint32_t)eq_run(eq[i], 0, c, reps[i], kMatchMaxLen);
+    }
+#pragma unroll
+    for (int i = 1; i < 4; i++)
+        if (rep_lens[i] > rep_lens[rep_max_index]) rep_max_index = i;
     if ((int)rep_lens[rep_max_index] >= fb) {  // :400-404
         const int len_res = (int)rep_lens[rep_max_index];
         *back_out = (uint32_t)rep_max_index;
@@ -523,32 +660,25 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
         return len_main;
     }
 
-    uint32_t current_byte = byte_at(-1);
-    uint32_t match_byte = byte_at(0 - (int)rep_dist[0] - 1 - 1);
+    uint32_t current_byte = __shfl_sync(kFull, a_byte, 0);
+    uint32_t match_byte = __shfl_sync(kFull, b_byte[0], 0);
 
     if (len_main < 2 && current_byte != match_byte && rep_lens[rep_max_index] < 2) {  // :415-417
-        *back_out = 0xFFFFFFFFu;
+        *back_out = kLit;
         return 1;
     }
 
     uint32_t pos_state = position & pos_mask;
-    {
-        OptNode* o0 = &opt[0];
-        o0->link = mk_link(0, 0, false, false) | ((uint32_t)state << 24);
-        o0->backs[0] = reps[0];
-        o0->backs[1] = reps[1];
-        o0->backs[2] = reps[2];
-        o0->backs[3] = reps[3];
-    }
-    uint32_t price1_ = price0(*p_is_match(state, pos_state)) +
-                       lit_price(lit_coder(position, prev_byte), !st_is_char(state), match_byte, current_byte);
-    uint32_t back1 = 0xFFFFFFFFu;  // MakeAsChar
+    int st = state;
+    uint32_t price1_ = price0(*p_is_match(st, pos_state)) +
+                       lit_price(lit_coder(position, prev_byte), !st_is_char(st), match_byte, current_byte);
+    uint32_t back1 = kLit;  // MakeAsChar
 
-    uint32_t match_price = price1(*p_is_match(state, pos_state));
-    uint32_t rep_match_price = match_price + price1(*p_is_rep(state));
+    uint32_t match_price = price1(*p_is_match(st, pos_state));
+    uint32_t rep_match_price = match_price + price1(*p_is_rep(st));
 
     if (match_byte == current_byte) {  // :430-436
-        const uint32_t short_rep_price = rep_match_price + rep_len1_price(state, pos_state);
+        const uint32_t short_rep_price = rep_match_price + rep_len1_price(st, pos_state);
         if (short_rep_price < price1_) {
             price1_ = short_rep_price;
             back1 = 0;  // MakeAsShortRep
@@ -560,85 +690,102 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
         *back_out = back1;
         return 1;
     }
-    opt[1].price = price1_;
-    opt[1].back_prev = back1;
-    opt[1].link = mk_link(0, 0, false, false);
+    int wb = 0;  // nodes [0, wb) live in gopt, the rest in the ring
+    __syncwarp();
+    if (lane == 0) {
+        OptNode* o0 = node(0);
+        o0->link = (uint32_t)st << 24;
+        o0->backs[0] = reps[0];
+        o0->backs[1] = reps[1];
+        o0->backs[2] = reps[2];
+        o0->backs[3] = reps[3];
+        OptNode* o1 = node(1);
+        o1->price = price1_;
+        o1->back_prev = back1;
+        o1->link = mk_link(0, 0, false, false);
+    }
+    for (int len = 2 + lane; len <= len_end; len += 32) node(len)->price = kInfinityPrice;  // :451-455
+    __syncwarp();
 
-    for (int len = len_end; len >= 2; len--) opt[len].price = kInfinityPrice;  // :451-455
-
-    for (int i = 0; i < kNumRepDistances; i++) {  // :457-474
-        int rep_len = (int)rep_lens[i];
+    for (int i = 0; i < kNumRepDistances; i++) {  // :457-474, one length per lane
+        const int rep_len = (int)rep_lens[i];
         if (rep_len < 2) continue;
-        const uint32_t price = rep_match_price + pure_rep_price(i, state, pos_state);
-        do {
-            relax(rep_len, price + len_price(1, rep_len - 2, pos_state), 0, (uint32_t)i, false, false, 0, 0);
-        } while (--rep_len >= 2);
+        const uint32_t price = rep_match_price + pure_rep_price(i, st, pos_state);
+        for (int len = 2 + lane; len <= rep_len; len += 32)
+            relax(len, price + len_price(1, len - 2, pos_state), 0, (uint32_t)i, false, false, 0, 0);
+        __syncwarp();
     }
 
-    uint32_t normal_match_price = match_price + price0(*p_is_rep(state));
-
+    uint32_t normal_match_price = match_price + price0(*p_is_rep(st));
     {
-        int len = rep_lens[0] >= 2 ? (int)rep_lens[0] + 1 : 2;  // :478-501
-        if (len <= len_main) {
+        const int start = rep_lens[0] >= 2 ? (int)rep_lens[0] + 1 : 2;  // :478-501
+        for (int len = start + lane; len <= len_main; len += 32) {
             int offs = 0;
             while (len > md_len(offs)) offs++;
-            for (;; len++) {
-                const uint32_t distance = md_dist(offs);
-                relax(len, normal_match_price + pos_len_price(distance, len, pos_state), 0, distance + kNumRepDistances,
-                      false, false, 0, 0);
-                if (len == md_len(offs)) {
-                    offs++;
-                    if (offs == num_distance_pairs) break;
-                }
-            }
+            const uint32_t distance = md_dist(offs);
+            relax(len, normal_match_price + pos_len_price(distance, len, pos_state), 0, distance + kNumRepDistances, false, false,
+                  0, 0);
         }
+        __syncwarp();
     }
 
     int cur = 0;
+    uint32_t last_byte = current_byte;  // data[c] of the previous step
     for (;;) {  // :505-810
         cur++;
-        if (cur == len_end) return backward(cur, back_out);
+        if (cur == len_end) return backward(cur, wb, back_out);
         int new_len = read_match_distances();
         num_distance_pairs = num_pairs;
         if (new_len >= fb) {
             longest_len = new_len;
             longest_found = true;
-            return backward(cur, back_out);
+            return backward(cur, wb, back_out);
         }
         position++;
-        OptNode* oc = &opt[cur];
-        const uint32_t clink = oc->link;
+        c = m - 1;
+
+        // ---- gather: window bytes + rep comparisons; issued before the node logic to overlap latency
+        const bool inr = c + lane < n;
+        a_byte = 0;
+        if (inr) a_byte = data[c + lane];
+
+        // ---- node cur -> state, reps (:518-590)
+        OptNode* oc = node(cur);
+        const uint4 ca = *reinterpret_cast<const uint4*>(oc);  // price, back_prev, back_prev2, link
+        const uint32_t clink = ca.w;
         uint32_t pos_prev = ln_pos_prev(clink);
-        int st;
-        if (ln_prev1(clink)) {  // :520-535
+        if (ln_prev1(clink)) {
             pos_prev--;
             if (ln_prev2(clink)) {
-                st = ln_state(opt[ln_pos_prev2(clink)].link);
-                if (oc->back_prev2 < kNumRepDistances) st = st_longrep(st);
+                st = ln_state(node((int)ln_pos_prev2(clink))->link);
+                if (ca.z < kNumRepDistances) st = st_longrep(st);
                 else st = st_match(st);
             } else {
-                st = ln_state(opt[pos_prev].link);
+                st = ln_state(node((int)pos_prev)->link);
             }
             st = st_lit(st);
         } else {
-            st = ln_state(opt[pos_prev].link);
+            st = ln_state(node((int)pos_prev)->link);
         }
-        if (pos_prev == (uint32_t)cur - 1) {  // :536-541
-            if (oc->back_prev == 0) st = st_shortrep(st);
+        if (pos_prev == (uint32_t)cur - 1) {
+            if (ca.y == 0) st = st_shortrep(st);
             else st = st_lit(st);
-        } else {  // :542-585
+            // reps stay those of the previous step only if that step was cur - 1's node; reload to be exact
+            const uint4 pb_ = *reinterpret_cast<const uint4*>(node((int)pos_prev)->backs);
+            reps[0] = pb_.x; reps[1] = pb_.y; reps[2] = pb_.z; reps[3] = pb_.w;
+        } else {
             uint32_t pos;
             if (ln_prev1(clink) && ln_prev2(clink)) {
                 pos_prev = ln_pos_prev2(clink);
-                pos = oc->back_prev2;
+                pos = ca.z;
                 st = st_longrep(st);
             } else {
-                pos = oc->back_prev;
+                pos = ca.y;
                 if (pos < kNumRepDistances) st = st_longrep(st);
                 else st = st_match(st);
             }
-            const OptNode* o = &opt[pos_prev];
-            const uint32_t b0 = o->backs[0], b1 = o->backs[1], b2 = o->backs[2], b3 = o->backs[3];
+            const uint4 pb_ = *reinterpret_cast<const uint4*>(node((int)pos_prev)->backs);
+            const uint32_t b0 = pb_.x, b1 = pb_.y, b2 = pb_.z, b3 = pb_.w;
             if (pos < kNumRepDistances) {
                 if (pos == 0) { reps[0] = b0; reps[1] = b1; reps[2] = b2; reps[3] = b3; }
                 else if (pos == 1) { reps[0] = b1; reps[1] = b0; reps[2] = b2; reps[3] = b3; }
@@ -651,165 +798,246 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
                 reps[3] = b2;
             }
         }
-        oc->link = (clink & ~(0xFu << 24)) | ((uint32_t)st << 24);
-        oc->backs[0] = reps[0];
-        oc->backs[1] = reps[1];
-        oc->backs[2] = reps[2];
-        oc->backs[3] = reps[3];
-        const uint32_t cur_price = oc->price;
-
-        current_byte = byte_at(-1);
-        match_byte = byte_at(0 - (int)reps[0] - 1 - 1);
-        pos_state = position & pos_mask;
-
-        const uint32_t cur_and1_price = cur_price + price0(*p_is_match(st, pos_state)) +
-                                        lit_price(lit_coder(position, byte_at(-2)), !st_is_char(st), match_byte, current_byte);
-
-        OptNode* next = &opt[cur + 1];
-        bool next_is_char = false;
-        if (cur_and1_price < next->price) {  // :606-611
-            next->price = cur_and1_price;
-            next->back_prev = 0xFFFFFFFFu;
-            next->link = mk_link((uint32_t)cur, 0, false, false);
-            next_is_char = true;
+        if (lane == 0) {
+            oc->link = (clink & ~(0xFu << 24)) | ((uint32_t)st << 24);
+            *reinterpret_cast<uint4*>(oc->backs) = make_uint4(reps[0], reps[1], reps[2], reps[3]);
         }
+        const uint32_t cur_price = ca.x;
 
-        match_price = cur_price + price1(*p_is_match(st, pos_state));
-        rep_match_price = match_price + price1(*p_is_rep(st));
-
-        if (match_byte == current_byte && !(ln_pos_prev(next->link) < (uint32_t)cur && next->back_prev == 0)) {  // :616-625
-            const uint32_t short_rep_price = rep_match_price + rep_len1_price(st, pos_state);
-            if (short_rep_price <= next->price) {
-                next->price = short_rep_price;
-                next->back_prev = 0;
-                next->link = mk_link((uint32_t)cur, 0, false, false);
-                next_is_char = true;
-            }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            b_byte[i] = 1;
+            if (inr) b_byte[i] = data[c + lane - reps[i] - 1];
         }
 
         int num_avail_full = avail() + 1;  // :627-636
         if (kNumOpts - 1 - cur < num_avail_full) num_avail_full = kNumOpts - 1 - cur;
-        num_avail = num_avail_full;
-        if (num_avail < 2) continue;
-        if (num_avail > fb) num_avail = fb;
+        num_avail = num_avail_full < fb ? num_avail_full : fb;
 
-        if (!next_is_char && match_byte != current_byte) {  // :637-665  literal + rep0
-            const int t = num_avail_full - 1 < fb ? num_avail_full - 1 : fb;
-            const int len_test2 = match_len(0, reps[0], t);
-            if (len_test2 >= 2) {
-                const int state2 = st_lit(st);
-                const uint32_t ps_next = (position + 1) & pos_mask;
-                const uint32_t next_rep_match_price = cur_and1_price + price1(*p_is_match(state2, ps_next)) + price1(*p_is_rep(state2));
-                const int offset = cur + 1 + len_test2;
-                while (len_end < offset) opt[++len_end].price = kInfinityPrice;
-                relax(offset, next_rep_match_price + rep_price(0, len_test2, state2, ps_next), (uint32_t)cur + 1, 0, true,
-                      false, 0, 0);
-            }
-        }
-
-        int start_len = 2;
-
-        for (int rep_index = 0; rep_index < kNumRepDistances; rep_index++) {  // :669-735
-            int len_test = match_len(-1, reps[rep_index], num_avail);
-            if (len_test < 2) continue;
-            const int len_test_temp = len_test;
-            const uint32_t rp = rep_match_price + pure_rep_price(rep_index, st, pos_state);
-            do {
-                while (len_end < cur + len_test) opt[++len_end].price = kInfinityPrice;
-                relax(cur + len_test, rp + len_price(1, len_test - 2, pos_state), (uint32_t)cur, (uint32_t)rep_index, false,
-                      false, 0, 0);
-            } while (--len_test >= 2);
-            len_test = len_test_temp;
-
-            if (rep_index == 0) start_len = len_test + 1;
-
-            if (len_test < num_avail_full) {  // :696-734  rep + literal + rep0
-                const int t = num_avail_full - 1 - len_test < fb ? num_avail_full - 1 - len_test : fb;
-                const int len_test2 = match_len(len_test, reps[rep_index], t);
-                if (len_test2 >= 2) {
-                    int state2 = st_longrep(st);
-                    uint32_t ps_next = (position + len_test) & pos_mask;
-                    const uint32_t cur_and_len_char_price =
-                        rp + len_price(1, len_test - 2, pos_state) + price0(*p_is_match(state2, ps_next)) +
-                        lit_price(lit_coder(position + len_test, byte_at(len_test - 1 - 1)), true,
-                                  byte_at(len_test - 1 - ((int)reps[rep_index] + 1)), byte_at(len_test - 1));
-                    state2 = st_lit(state2);
-                    ps_next = (position + len_test + 1) & pos_mask;
-                    const uint32_t next_match_price = cur_and_len_char_price + price1(*p_is_match(state2, ps_next));
-                    const uint32_t next_rep_match_price = next_match_price + price1(*p_is_rep(state2));
-                    const int offset = len_test + 1 + len_test2;
-                    while (len_end < cur + offset) opt[++len_end].price = kInfinityPrice;
-                    relax(cur + offset, next_rep_match_price + rep_price(0, len_test2, state2, ps_next),
-                          (uint32_t)(cur + len_test + 1), 0, true, true, (uint32_t)cur, (uint32_t)rep_index);
+        // match + literal + rep0 continuations of this position's pairs (:766-770): two bytes per lane and pair
+        if (num_avail_full >= 2 && num_distance_pairs > 0) {
+            for (int j0 = 0; j0 < num_distance_pairs; j0 += 4) {
+                uint32_t xa[4], xb[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int j = j0 + u;
+                    xa[u] = 0;
+                    xb[u] = 1;
+                    if (j < num_distance_pairs) {
+                        int lj = md_len(j);
+                        if (lj > num_avail) lj = num_avail;  // the truncation of :737-743
+                        const uint32_t s = c + lj + 1 + lane;
+                        if (s < n) {
+                            xa[u] = data[s];
+                            xb[u] = data[s - md_dist(j) - 1];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int j = j0 + u;
+                    const unsigned e = __ballot_sync(kFull, xa[u] == xb[u]);
+                    if (j < num_distance_pairs) {
+                        int lj = md_len(j);
+                        if (lj > num_avail) lj = num_avail;
+                        int l2 = 0;
+                        if (lj < num_avail_full) {
+                            const int t = num_avail_full - 1 - lj < fb ? num_avail_full - 1 - lj : fb;
+                            l2 = eq_run(e, 0, c + lj + 1, md_dist(j), t);
+                        }
+                        if (lane == 0) md2[j] = (uint16_t)l2;
+                    }
                 }
             }
         }
 
+#pragma unroll
+        for (int i = 0; i < 4; i++) eq[i] = __ballot_sync(kFull, inr && a_byte == b_byte[i]);
+        current_byte = __shfl_sync(kFull, a_byte, 0);
+        match_byte = __shfl_sync(kFull, b_byte[0], 0);
+        pos_state = position & pos_mask;
+
+        // ---- literal and short rep into node cur + 1 (:598-625)
+        const uint32_t cur_and1_price = cur_price + price0(*p_is_match(st, pos_state)) +
+                                        lit_price(lit_coder(position, last_byte), !st_is_char(st), match_byte, current_byte);
+        last_byte = current_byte;
+        OptNode* next = node(cur + 1);
+        uint32_t n_price = next->price, n_back = next->back_prev, n_link = next->link;
+        bool next_is_char = false, n_dirty = false;
+        if (cur_and1_price < n_price) {
+            n_price = cur_and1_price;
+            n_back = kLit;
+            n_link = mk_link((uint32_t)cur, 0, false, false);
+            next_is_char = true;
+            n_dirty = true;
+        }
+        match_price = cur_price + price1(*p_is_match(st, pos_state));
+        rep_match_price = match_price + price1(*p_is_rep(st));
+        if (match_byte == current_byte && !(ln_pos_prev(n_link) < (uint32_t)cur && n_back == 0)) {
+            const uint32_t short_rep_price = rep_match_price + rep_len1_price(st, pos_state);
+            if (short_rep_price <= n_price) {
+                n_price = short_rep_price;
+                n_back = 0;
+                n_link = mk_link((uint32_t)cur, 0, false, false);
+                next_is_char = true;
+                n_dirty = true;
+            }
+        }
+        if (n_dirty && lane == 0) {
+            next->price = n_price;
+            next->back_prev = n_back;
+            next->link = n_link;
+        }
+        if (num_avail_full < 2) continue;
+
+        // ---- rep lengths and every continuation length, then one extension of the node range
+        int len_test[4], len_test2[4];
+        int need = len_end;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            len_test[i] = eq_run(eq[i], 0, c, reps[i], num_avail);
+            len_test2[i] = 0;
+            if (len_test[i] >= 2) {
+                if (cur + len_test[i] > need) need = cur + len_test[i];
+                if (len_test[i] < num_avail_full) {
+                    const int t = num_avail_full - 1 - len_test[i] < fb ? num_avail_full - 1 - len_test[i] : fb;
+                    len_test2[i] = eq_run(eq[i], len_test[i] + 1, c, reps[i], t);
+                    if (len_test2[i] >= 2 && cur + len_test[i] + 1 + len_test2[i] > need) need = cur + len_test[i] + 1 + len_test2[i];
+                }
+            }
+        }
+        int lit_rep0_len = 0;
+        if (!next_is_char && match_byte != current_byte) {  // :637-641
+            const int t = num_avail_full - 1 < fb ? num_avail_full - 1 : fb;
+            lit_rep0_len = eq_run(eq[0], 1, c, reps[0], t);
+            if (lit_rep0_len >= 2 && cur + 1 + lit_rep0_len > need) need = cur + 1 + lit_rep0_len;
+        }
+        const int start_len = len_test[0] >= 2 ? len_test[0] + 1 : 2;  // :667, :691-693
         if (new_len > num_avail) {  // :737-743
             new_len = num_avail;
             for (num_distance_pairs = 0; new_len > md_len(num_distance_pairs); num_distance_pairs++) {}
-            md[num_distance_pairs] = ((uint32_t)new_len << kPairDistBits) | md_dist(num_distance_pairs);
+            __syncwarp();
+            if (lane == 0) md[num_distance_pairs] = ((uint32_t)new_len << kPairDistBits) | md_dist(num_distance_pairs);
             num_distance_pairs++;
+            __syncwarp();
         }
-        if (new_len >= start_len) {  // :744-809
-            normal_match_price = match_price + price0(*p_is_rep(st));
-            while (len_end < cur + new_len) opt[++len_end].price = kInfinityPrice;
-
-            int offs = 0;
-            while (start_len > md_len(offs)) offs++;
-
-            for (int len_test = start_len;; len_test++) {
-                const uint32_t cur_back = md_dist(offs);
-                uint32_t cur_and_len_price = normal_match_price + pos_len_price(cur_back, len_test, pos_state);
-                relax(cur + len_test, cur_and_len_price, (uint32_t)cur, cur_back + kNumRepDistances, false, false, 0, 0);
-
-                if (len_test == md_len(offs)) {
-                    if (len_test < num_avail_full) {  // match + literal + rep0
-                        const int t = num_avail_full - 1 - len_test < fb ? num_avail_full - 1 - len_test : fb;
-                        const int len_test2 = match_len(len_test, cur_back, t);
-                        if (len_test2 >= 2) {
-                            int state2 = st_match(st);
-                            uint32_t ps_next = (position + len_test) & pos_mask;
-                            const uint32_t cur_and_len_char_price =
-                                cur_and_len_price + price0(*p_is_match(state2, ps_next)) +
-                                lit_price(lit_coder(position + len_test, byte_at(len_test - 1 - 1)), true,
-                                          byte_at(len_test - ((int)cur_back + 1) - 1), byte_at(len_test - 1));
-                            state2 = st_lit(state2);
-                            ps_next = (position + len_test + 1) & pos_mask;
-                            const uint32_t next_match_price = cur_and_len_char_price + price1(*p_is_match(state2, ps_next));
-                            const uint32_t next_rep_match_price = next_match_price + price1(*p_is_rep(state2));
-                            const int offset = len_test + 1 + len_test2;
-                            while (len_end < cur + offset) opt[++len_end].price = kInfinityPrice;
-                            cur_and_len_price = next_rep_match_price + rep_price(0, len_test2, state2, ps_next);
-                            relax(cur + offset, cur_and_len_price, (uint32_t)(cur + len_test + 1), 0, true, true, (uint32_t)cur,
-                                  cur_back + kNumRepDistances);
-                        }
-                    }
-                    offs++;
-                    if (offs == num_distance_pairs) break;
-                }
+        const bool do_matches = new_len >= start_len;
+        if (do_matches) {
+            if (cur + new_len > need) need = cur + new_len;
+            __syncwarp();  // md2 written above
+            for (int j = 0; j < num_distance_pairs; j++) {
+                const int lj = md_len(j);
+                if (lj < start_len) continue;
+                const int l2 = md2[j];
+                if (l2 >= 2 && cur + lj + 1 + l2 > need) need = cur + lj + 1 + l2;
             }
+        }
+        extend(len_end, wb, need);
+        __syncwarp();
+
+        // ---- literal + rep0 (:642-664)
+        if (lit_rep0_len >= 2) {
+            const int state2 = st_lit(st);
+            const uint32_t ps_next = (position + 1) & pos_mask;
+            const uint32_t next_rep_match_price = cur_and1_price + price1(*p_is_match(state2, ps_next)) + price1(*p_is_rep(state2));
+            if (lane == 0)
+                relax(cur + 1 + lit_rep0_len, next_rep_match_price + rep_price(0, lit_rep0_len, state2, ps_next), (uint32_t)cur + 1, 0,
+                      true, false, 0, 0);
+            __syncwarp();
+        }
+
+        // ---- reps (:669-735)
+#pragma unroll
+        for (int rep_index = 0; rep_index < kNumRepDistances; rep_index++) {
+            const int lt = len_test[rep_index];
+            if (lt < 2) continue;
+            const uint32_t rp = rep_match_price + pure_rep_price(rep_index, st, pos_state);
+            for (int len = 2 + lane; len <= lt; len += 32)
+                relax(cur + len, rp + len_price(1, len - 2, pos_state), (uint32_t)cur, (uint32_t)rep_index, false, false, 0, 0);
+            __syncwarp();
+            const int lt2 = len_test2[rep_index];
+            if (lt2 >= 2) {  // rep + literal + rep0 (:696-734)
+                int state2 = st_longrep(st);
+                uint32_t ps_next = (position + lt) & pos_mask;
+                uint32_t sym, prv, mb;
+                if (lt < 32) {
+                    sym = __shfl_sync(kFull, a_byte, lt);
+                    prv = __shfl_sync(kFull, a_byte, lt - 1);
+                    mb = __shfl_sync(kFull, b_byte[rep_index], lt);
+                } else {
+                    sym = data[c + lt];
+                    prv = data[c + lt - 1];
+                    mb = data[c + lt - reps[rep_index] - 1];
+                }
+                const uint32_t cur_and_len_char_price = rp + len_price(1, lt - 2, pos_state) + price0(*p_is_match(state2, ps_next)) +
+                                                        lit_price(lit_coder(position + lt, prv), true, mb, sym);
+                state2 = st_lit(state2);
+                ps_next = (position + lt + 1) & pos_mask;
+                const uint32_t next_match_price = cur_and_len_char_price + price1(*p_is_match(state2, ps_next));
+                const uint32_t next_rep_match_price = next_match_price + price1(*p_is_rep(state2));
+                if (lane == 0)
+                    relax(cur + lt + 1 + lt2, next_rep_match_price + rep_price(0, lt2, state2, ps_next), (uint32_t)(cur + lt + 1), 0,
+                          true, true, (uint32_t)cur, (uint32_t)rep_index);
+                __syncwarp();
+            }
+        }
+
+        // ---- matches (:744-809).  A node X = cur + L can be reached by the plain match of length L
+        // and by "match l + literal + rep0" with l < L; the reference applies the latter first
+        // (they come up at the pair boundary l), so all continuations go first, in pair order.
+        if (do_matches) {
+            normal_match_price = match_price + price0(*p_is_rep(st));
+            for (int j = 0; j < num_distance_pairs; j++) {
+                const int lj = md_len(j);
+                if (lj < start_len) continue;
+                const int l2 = md2[j];
+                if (l2 < 2) continue;
+                const uint32_t cur_back = md_dist(j);
+                const uint32_t cur_and_len_price = normal_match_price + pos_len_price(cur_back, lj, pos_state);
+                int state2 = st_match(st);
+                uint32_t ps_next = (position + lj) & pos_mask;
+                const uint32_t sym = data[c + lj], prv = data[c + lj - 1], mb = data[c + lj - cur_back - 1];
+                const uint32_t cur_and_len_char_price = cur_and_len_price + price0(*p_is_match(state2, ps_next)) +
+                                                        lit_price(lit_coder(position + lj, prv), true, mb, sym);
+                state2 = st_lit(state2);
+                ps_next = (position + lj + 1) & pos_mask;
+                const uint32_t next_match_price = cur_and_len_char_price + price1(*p_is_match(state2, ps_next));
+                const uint32_t next_rep_match_price = next_match_price + price1(*p_is_rep(state2));
+                if (lane == 0)
+                    relax(cur + lj + 1 + l2, next_rep_match_price + rep_price(0, l2, state2, ps_next), (uint32_t)(cur + lj + 1), 0, true,
+                          true, (uint32_t)cur, cur_back + kNumRepDistances);
+                __syncwarp();
+            }
+            for (int len = start_len + lane; len <= new_len; len += 32) {
+                int offs = 0;
+                while (len > md_len(offs)) offs++;
+                const uint32_t cur_back = md_dist(offs);
+                relax(cur + len, normal_match_price + pos_len_price(cur_back, len, pos_state), (uint32_t)cur, cur_back + kNumRepDistances,
+                      false, false, 0, 0);
+            }
+            __syncwarp();
         }
     }
 }
 
-__device__ void Enc::write_end_marker(uint32_t ps) {  // Encoder.java:818-835
-    if (!eos) return;
-    rc.encode(p_is_match(state, ps), 1);
-    rc.encode(p_is_rep(state), 0);
-    state = st_match(state);
-    len_encode(0, 0, ps);
-    const uint32_t slot = (1u << kNumPosSlotBits) - 1;
-    rc.tree(model + L.pos_slot + (len_to_pos_state(kMatchMinLen) << kNumPosSlotBits), kNumPosSlotBits, slot);
-    const int footer_bits = 30;
-    const uint32_t pos_reduced = (1u << footer_bits) - 1;
-    rc.direct(pos_reduced >> kNumAlignBits, footer_bits - kNumAlignBits);
-    rc.reverse(model + L.pos_align, kNumAlignBits, pos_reduced & kAlignMask);
-}
-
-__device__ void Enc::flush_stream(uint32_t now) {  // :837-841
-    write_end_marker(now & pos_mask);
-    rc.flush();
+__device__ void Enc::flush_stream(uint32_t now) {  // Encoder.java:837-841 + WriteEndMarker :818-835
+    const uint32_t ps = now & pos_mask;
+    if (lane == 0) {
+        if (eos) {
+            rc.encode(p_is_match(state, ps), 1);
+            rc.encode(p_is_rep(state), 0);
+            len_encode_bits(0, 0, ps);
+            const uint32_t slot = (1u << kNumPosSlotBits) - 1;
+            rc.tree(model + L.pos_slot + (len_to_pos_state(kMatchMinLen) << kNumPosSlotBits), kNumPosSlotBits, slot);
+            const int footer_bits = 30;
+            const uint32_t pos_reduced = (1u << footer_bits) - 1;
+            rc.direct(pos_reduced >> kNumAlignBits, footer_bits - kNumAlignBits);
+            rc.reverse(model + L.pos_align, kNumAlignBits, pos_reduced & kAlignMask);
+        }
+        rc.flush();
+    }
+    if (eos) state = st_match(state);
+    __syncwarp();
 }
 
 // encodeOne (:890-936) with its emitters (:938-1024); false once the stream is flushed
@@ -817,64 +1045,79 @@ __device__ bool Enc::encode_one() {
     uint32_t back;
     const int len = get_optimum(now_pos, &back);
     const uint32_t ps = now_pos & pos_mask;
-    if (len == 1 && back == 0xFFFFFFFFu) {
-        rc.encode(p_is_match(state, ps), 0);
+    __syncwarp();
+    if (len == 1 && back == kLit) {
         const uint32_t cur_byte = byte_at(0 - additional_offset);  // encodeSingleByteLiteral :1007-1024
-        uint16_t* sub = lit_coder(now_pos, prev_byte);
-        if (st_is_char(state)) {
-            lit_encode(sub, cur_byte);
-        } else {
-            const uint32_t mb = byte_at(0 - (int)rep_dist[0] - 1 - additional_offset);
-            lit_encode_matched(sub, mb, cur_byte);
+        if (lane == 0) {
+            rc.encode(p_is_match(state, ps), 0);
+            uint16_t* sub = lit_coder(now_pos, prev_byte);
+            if (st_is_char(state)) {
+                lit_encode(sub, cur_byte);
+            } else {
+                const uint32_t mb = byte_at(0 - (int)rep_dist[0] - 1 - additional_offset);
+                lit_encode_matched(sub, mb, cur_byte);
+            }
         }
         prev_byte = cur_byte;
         state = st_lit(state);
+        __syncwarp();
     } else {
-        rc.encode(p_is_match(state, ps), 1);
         if (back < kNumRepDistances) {  // encodeARepetition :938-974
-            rc.encode(p_is_rep(state), 1);
-            if (back == 0) {
-                rc.encode(p_is_rep_g0(state), 0);
-                rc.encode(p_is_rep0_long(state, ps), len == 1 ? 0 : 1);
-            } else {
-                rc.encode(p_is_rep_g0(state), 1);
-                if (back == 1) {
-                    rc.encode(p_is_rep_g1(state), 0);
+            if (lane == 0) {
+                rc.encode(p_is_match(state, ps), 1);
+                rc.encode(p_is_rep(state), 1);
+                if (back == 0) {
+                    rc.encode(p_is_rep_g0(state), 0);
+                    rc.encode(p_is_rep0_long(state, ps), len == 1 ? 0 : 1);
                 } else {
-                    rc.encode(p_is_rep_g1(state), 1);
-                    rc.encode(p_is_rep_g2(state), back - 2);
+                    rc.encode(p_is_rep_g0(state), 1);
+                    if (back == 1) {
+                        rc.encode(p_is_rep_g1(state), 0);
+                    } else {
+                        rc.encode(p_is_rep_g1(state), 1);
+                        rc.encode(p_is_rep_g2(state), back - 2);
+                    }
                 }
+                if (len != 1) len_encode_bits(1, len - kMatchMinLen, ps);
             }
+            __syncwarp();
             if (len == 1) {
                 state = st_shortrep(state);
             } else {
-                len_encode(1, len - kMatchMinLen, ps);
+                len_count(1, ps);
                 state = st_longrep(state);
             }
             const uint32_t distance = rep_dist[back];
             if (back != 0) {
-                for (int k = (int)back; k >= 1; k--) rep_dist[k] = rep_dist[k - 1];
+                if (back == 3) rep_dist[3] = rep_dist[2];
+                if (back >= 2) rep_dist[2] = rep_dist[1];
+                rep_dist[1] = rep_dist[0];
                 rep_dist[0] = distance;
             }
         } else {  // encodeAMatch :976-1005
-            rc.encode(p_is_rep(state), 0);
-            state = st_match(state);
-            len_encode(0, len - kMatchMinLen, ps);
             const uint32_t pos = back - kNumRepDistances;
             const int slot = pos_slot(pos);
-            rc.tree(model + L.pos_slot + (len_to_pos_state(len) << kNumPosSlotBits), kNumPosSlotBits, slot);
-            if (slot >= kStartPosModelIndex) {
-                const int footer_bits = (slot >> 1) - 1;
-                const uint32_t base = (2u | (slot & 1)) << footer_bits;
-                const uint32_t pos_reduced = pos - base;
-                if (slot < kEndPosModelIndex) {
-                    rc.reverse(model + L.pos_dec + base - slot - 1, footer_bits, pos_reduced);
-                } else {
-                    rc.direct(pos_reduced >> kNumAlignBits, footer_bits - kNumAlignBits);
-                    rc.reverse(model + L.pos_align, kNumAlignBits, pos_reduced & kAlignMask);
-                    align_price_count++;
+            if (lane == 0) {
+                rc.encode(p_is_match(state, ps), 1);
+                rc.encode(p_is_rep(state), 0);
+                len_encode_bits(0, len - kMatchMinLen, ps);
+                rc.tree(model + L.pos_slot + (len_to_pos_state(len) << kNumPosSlotBits), kNumPosSlotBits, slot);
+                if (slot >= kStartPosModelIndex) {
+                    const int footer_bits = (slot >> 1) - 1;
+                    const uint32_t base = (2u | (slot & 1)) << footer_bits;
+                    const uint32_t pos_reduced = pos - base;
+                    if (slot < kEndPosModelIndex) {
+                        rc.reverse(model + L.pos_dec + base - slot - 1, footer_bits, pos_reduced);
+                    } else {
+                        rc.direct(pos_reduced >> kNumAlignBits, footer_bits - kNumAlignBits);
+                        rc.reverse(model + L.pos_align, kNumAlignBits, pos_reduced & kAlignMask);
+                    }
                 }
             }
+            __syncwarp();
+            state = st_match(state);
+            len_count(0, ps);
+            if (slot >= kEndPosModelIndex) align_price_count++;
             rep_dist[3] = rep_dist[2];
             rep_dist[2] = rep_dist[1];
             rep_dist[1] = rep_dist[0];
@@ -902,11 +1145,17 @@ __device__ void Enc::run() {
     prev_byte = 0;
     for (int i = 0; i < 4; i++) rep_dist[i] = 0;
     longest_found = false;
+    longest_len = 0;
     opt_end = opt_cur = 0;
     additional_offset = 0;
     m = 0;
+    pre_pos = 0;
+    pre_off = kMfEmpty;
     now_pos = 0;
     num_pairs = 0;
+    match_price_count = 0;
+    align_price_count = 0;
+    qbase = ring;
     fill_distances_prices();
     fill_align_prices();
     for (int which = 0; which < 2; which++)
@@ -917,10 +1166,13 @@ __device__ void Enc::run() {
         return;
     }
     read_match_distances();  // first byte is always a plain literal (:860-878)
-    rc.encode(p_is_match(state, 0), 0);
-    state = st_lit(state);
     const uint32_t cur_byte = byte_at(0 - additional_offset);
-    lit_encode(lit_coder(0, prev_byte), cur_byte);
+    if (lane == 0) {
+        rc.encode(p_is_match(state, 0), 0);
+        lit_encode(lit_coder(0, prev_byte), cur_byte);
+    }
+    __syncwarp();
+    state = st_lit(state);
     prev_byte = cur_byte;
     additional_offset--;
     now_pos++;
@@ -931,50 +1183,17 @@ __device__ void Enc::run() {
     while (encode_one()) {}
 }
 
-// ---- shared-memory slice of one warp ----------------------------------------
-struct SliceLayout {
-    uint32_t model, dist_prices, slot_prices, align_prices, len_prices, len_counters, md, total;  // byte offsets
-    bool lit_in_smem;
-};
-__host__ __device__ inline SliceLayout make_slice(int lc, int lp, int pb, int fb) {
-    SliceLayout s;
-    const ModelLayout L = make_layout(lc, lp, pb);
-    const uint32_t table = (uint32_t)(fb - 1);
-    auto fixed_after = [&](uint32_t o) {
-        SliceLayout r;
-        r.dist_prices = o;  o += 512 * 2;
-        r.slot_prices = o;  o += 256 * 2;
-        r.align_prices = o; o += 16 * 2;
-        r.len_prices = o;   o += ((2u << pb) * table * 2 + 3) & ~3u;
-        r.len_counters = o; o += 32 * 4;
-        r.md = o;           o += 276 * 4;
-        r.total = o;
-        return r;
-    };
-    uint32_t with_lit = (uint32_t)(L.n_fixed + L.n_literal) * 2;
-    SliceLayout a = fixed_after((with_lit + 15) & ~15u);
-    if (a.total <= kEncSliceBytes) {
-        s = a;
-        s.lit_in_smem = true;
-    } else {
-        s = fixed_after(((uint32_t)L.n_fixed * 2 + 15) & ~15u);
-        s.lit_in_smem = false;
-    }
-    s.model = 0;
-    return s;
-}
-
 __global__ void __launch_bounds__(kEncMaxWarps * 32, 1) lzb_parse_kernel(ParseArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CtaTables* tables = reinterpret_cast<CtaTables*>(smem_raw);
     init_cta_tables(tables);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;
-    uint8_t* slice = smem_raw + sizeof(CtaTables) + (size_t)warp * kEncSliceBytes;
+    uint8_t* slice = smem_raw + sizeof(CtaTables) + (size_t)warp * a.slice_bytes;
     const size_t slot = (size_t)blockIdx.x * warps + warp;
     const ModelLayout L = make_layout(a.lc, a.lp, a.pb);
-    const SliceLayout S = make_slice(a.lc, a.lp, a.pb, a.fb);
-    uint16_t* model = reinterpret_cast<uint16_t*>(slice + S.model);
+    const SliceLayout S = make_slice(a.lc, a.lp, a.pb, a.fb, a.slice_budget);
+    uint16_t* model = reinterpret_cast<uint16_t*>(slice);
     uint16_t* lit = S.lit_in_smem ? model + L.literal : a.lit_scratch + slot * (size_t)L.n_literal;
 
     for (;;) {
@@ -1004,60 +1223,72 @@ __global__ void __launch_bounds__(kEncMaxWarps * 32, 1) lzb_parse_kernel(ParseAr
             }
         }
         // Encoder.Init (:247-273): every probability = 1024; price tables start from Java's zero-init (App. A #14)
+        __syncwarp();
         for (int i = lane; i < L.n_fixed; i += 32) model[i] = kProbInit;
         for (int i = lane; i < L.n_literal; i += 32) lit[i] = kProbInit;
         {
             uint32_t* z = reinterpret_cast<uint32_t*>(slice + S.dist_prices);
-            const uint32_t words = (S.total - S.dist_prices) / 4;
+            const uint32_t words = (S.ring - S.dist_prices) / 4;
             for (uint32_t i = lane; i < words; i += 32) z[i] = 0;
         }
         __syncwarp();
-        if (lane == 0) {
-            Enc e;
-            e.T = tables;
-            e.model = model;
-            e.lit = lit;
-            e.dist_prices = reinterpret_cast<uint16_t*>(slice + S.dist_prices);
-            e.slot_prices = reinterpret_cast<uint16_t*>(slice + S.slot_prices);
-            e.align_prices = reinterpret_cast<uint16_t*>(slice + S.align_prices);
-            e.len_prices = reinterpret_cast<uint16_t*>(slice + S.len_prices);
-            e.len_counters = reinterpret_cast<int32_t*>(slice + S.len_counters);
-            e.md = reinterpret_cast<uint32_t*>(slice + S.md);
-            e.opt = reinterpret_cast<OptNode*>(a.opt_scratch) + slot * (size_t)kNumOpts;
-            e.L = L;
-            e.data = a.mf.in + a.mf.in_off[b];
-            e.n = n;
-            e.idx = a.mf.idx + (size_t)b * a.mf.np;
-            e.pairs = a.mf.pairs + (size_t)b * a.mf.pair_cap;
-            e.lc = a.lc;
-            e.lp = a.lp;
-            e.pb = a.pb;
-            e.fb = a.fb;
-            e.table_size = a.fb + 1 - kMatchMinLen;
-            e.dist_table_size = a.dist_table_size;
-            e.pos_mask = (1u << a.pb) - 1;
-            e.lp_mask = (1u << a.lp) - 1;
-            e.eos = a.eos;
-            e.match_price_count = 0;
-            e.align_price_count = 0;
-            e.rc.init(out, cap);
-            e.run();
-            a.out_len[b] = e.rc.pos > cap ? ~0ull : e.rc.pos + header;
-        }
+        Enc e;
+        e.T = tables;
+        e.model = model;
+        e.lit = lit;
+        e.dist_prices = reinterpret_cast<uint16_t*>(slice + S.dist_prices);
+        e.slot_prices = reinterpret_cast<uint16_t*>(slice + S.slot_prices);
+        e.align_prices = reinterpret_cast<uint16_t*>(slice + S.align_prices);
+        e.len_prices = reinterpret_cast<uint16_t*>(slice + S.len_prices);
+        e.len_counters = reinterpret_cast<int32_t*>(slice + S.len_counters);
+        e.md = reinterpret_cast<uint32_t*>(slice + S.md);
+        e.md2 = reinterpret_cast<uint16_t*>(slice + S.md2);
+        e.ring = reinterpret_cast<OptNode*>(slice + S.ring);
+        e.rmask = S.ring_nodes - 1;
+        e.gopt = reinterpret_cast<OptNode*>(a.opt_scratch) + slot * (size_t)kNumOpts;
+        e.L = L;
+        e.data = a.mf.in + a.mf.in_off[b];
+        e.n = n;
+        e.idx = a.mf.idx + (size_t)b * a.mf.np;
+        e.pairs = a.mf.pairs + (size_t)b * a.mf.pair_cap;
+        e.lane = lane;
+        e.lc = a.lc;
+        e.lp = a.lp;
+        e.pb = a.pb;
+        e.fb = a.fb;
+        e.table_size = a.fb + 1 - kMatchMinLen;
+        e.dist_table_size = a.dist_table_size;
+        e.pos_mask = (1u << a.pb) - 1;
+        e.lp_mask = (1u << a.lp) - 1;
+        e.eos = a.eos;
+        e.rc.init(out, cap);
+        e.run();
+        if (lane == 0) a.out_len[b] = e.rc.pos > cap ? ~0ull : e.rc.pos + header;
         __syncwarp();
     }
 }
 
-size_t parse_smem_bytes(int warps) { return sizeof(CtaTables) + (size_t)warps * kEncSliceBytes; }
-
-bool parse_lit_in_smem(int lc, int lp, int pb, int fb) { return make_slice(lc, lp, pb, fb).lit_in_smem; }
+// ---- host side ---------------------------------------------------------------
+ParseGeometry parse_geometry(int lc, int lp, int pb, int fb) {
+    ParseGeometry g;
+    const uint32_t usable = 232448 - (uint32_t)sizeof(CtaTables);
+    g.slice_budget = usable / 2;  // keep the literal coders in shared memory while two streams still fit an SM
+    const SliceLayout s = make_slice(lc, lp, pb, fb, g.slice_budget);
+    g.slice_bytes = (s.total + 127) & ~127u;
+    int warps = (int)(usable / g.slice_bytes);
+    if (warps > kEncMaxWarps) warps = kEncMaxWarps;
+    if (warps < 1) warps = 1;
+    g.max_warps = warps;
+    g.lit_in_smem = s.lit_in_smem;
+    g.cta_table_bytes = (uint32_t)sizeof(CtaTables);
+    return g;
+}
 
 size_t parse_opt_bytes_per_slot() { return sizeof(OptNode) * (size_t)kNumOpts; }
 
 cudaError_t launch_parse(const ParseArgs& a, int grid, int warps, cudaStream_t st) {
-    const size_t smem = parse_smem_bytes(warps);
-    cudaError_t e = cudaFuncSetAttribute(lzb_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)parse_smem_bytes(kEncMaxWarps));
+    const size_t smem = sizeof(CtaTables) + (size_t)warps * a.slice_bytes;
+    cudaError_t e = cudaFuncSetAttribute(lzb_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     lzb_parse_kernel<<<grid, warps * 32, smem, st>>>(a);
     return cudaGetLastError();
