@@ -146,7 +146,8 @@ int lzb_dec_code(lzb_dec *d, const uint8_t *in, uint64_t in_len,
 /* n independent LzmaAlone decodes (LzmaAlone.java:220-239): stream i is the
  * .lzma file in[in_off[i] .. +in_len[i]) whose own 13-byte header supplies
  * properties and size.  status[i] = 1 / 0 (reference true / false, or a
- * header the reference rejects) or LZB_E_CAPACITY; out_len[i] = bytes
+ * header the reference rejects), LZB_E_CAPACITY, or LZB_E_UNSUPPORTED for a
+ * stream of 4 GiB or more (positions are 32-bit in the kernel); out_len[i] = bytes
  * written at out[out_off[i] ..).  HOST pointers.  The call returns 1 if it
  * ran (inspect status[] per stream), < 0 on infrastructure errors. */
 int lzb_dec_code_batch(lzb_dec *d, const uint8_t *in, const uint64_t *in_off,

@@ -24,60 +24,63 @@ namespace lzb {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
+// Range decoder state of one stream, in lane 0's registers.  Every bit goes
+// through ONE code path (`bit`), and every multi-bit symbol through a rolled
+// loop around it, so that the whole kernel stays a few hundred instructions:
+// 15 warps per SM execute different parts of it at any time and the
+// instruction caches hold 32 KB.
 struct RangeDec {
-    uint32_t range, code, nextb;
-    const uint8_t* p;
-    const uint8_t* end;
+    uint32_t range, code, nextb, ip, len;
+    const uint8_t* in;
 
     // InputStream.read(): bytes past the end read as -1, which the reference
     // ORs into _code as all ones (RangeDecoder.java:23,36).
-    __device__ __forceinline__ void prefetch() { nextb = (p < end) ? (uint32_t)__ldg(p) : 0xFFFFFFFFu; }
-    __device__ __forceinline__ uint32_t read() {
-        uint32_t b = nextb;
-        ++p;
-        prefetch();
-        return b;
+    __device__ __forceinline__ void fetch() {
+        nextb = 0xFFFFFFFFu;
+        if (ip < len) nextb = __ldg(in + ip);
+        ip++;
     }
-    __device__ __forceinline__ void init(const uint8_t* in, const uint8_t* e) {  // RangeDecoder.java:19-25
-        p = in;
-        end = e;
+    __device__ __forceinline__ void init(const uint8_t* p, uint32_t n) {  // RangeDecoder.java:19-25
+        in = p;
+        len = n;
+        ip = 0;
         code = 0;
         range = 0xFFFFFFFFu;
-        prefetch();
-#pragma unroll
-        for (int i = 0; i < 5; i++) code = (code << 8) | read();
+        fetch();
+#pragma unroll 1
+        for (int i = 0; i < 5; i++) {
+            code = (code << 8) | nextb;
+            fetch();
+        }
     }
     __device__ __forceinline__ void normalize() {
         if (range < kTopValue) {
             range <<= 8;
-            code = (code << 8) | read();
+            code = (code << 8) | nextb;
+            fetch();
         }
     }
-    // RangeDecoder.DecodeBit (:43-64)
-    template <typename P>
-    __device__ __forceinline__ uint32_t bit(P* prob) {
-        uint32_t p0 = *prob;
-        uint32_t bound = (range >> kNumBitModelTotalBits) * p0;
-        uint32_t b;
-        if (code < bound) {
-            range = bound;
-            *prob = (uint16_t)(p0 + ((kBitModelTotal - p0) >> kNumMoveBits));
-            b = 0;
-        } else {
-            range -= bound;
-            code -= bound;
-            *prob = (uint16_t)(p0 - (p0 >> kNumMoveBits));
-            b = 1;
-        }
+    // RangeDecoder.DecodeBit (:43-64), branch-free:
+    //   bit 0: p += (2048 - p) >> 5      bit 1: p -= p >> 5
+    // are both  p -= (p - k) >> 5 (arithmetic shift) with k = 2017 (= 2048 - 31) resp. 0.
+    __device__ __forceinline__ uint32_t bit(uint16_t* prob) {
+        const uint32_t p0 = *prob;
+        const uint32_t bound = (range >> kNumBitModelTotalBits) * p0;
+        const bool one = code >= bound;
+        const int32_t k = one ? 0 : (kBitModelTotal - 31);
+        range = one ? range - bound : bound;
+        if (one) code -= bound;
+        *prob = (uint16_t)((int32_t)p0 - (((int32_t)p0 - k) >> kNumMoveBits));
         normalize();
-        return b;
+        return one ? 1u : 0u;
     }
     // RangeDecoder.DecodeDirectBits (:27-41)
     __device__ __forceinline__ uint32_t direct(int nbits) {
         uint32_t result = 0;
+#pragma unroll 1
         for (int i = nbits; i != 0; i--) {
             range >>= 1;
-            uint32_t t = (code - range) >> 31;
+            const uint32_t t = (code - range) >> 31;
             code -= range & (t - 1);
             result = (result << 1) | (1 - t);
             normalize();
@@ -85,18 +88,18 @@ struct RangeDec {
         return result;
     }
     // BitTreeDecoder.Decode (BitTreeDecoder.java:19-25)
-    template <int NBITS>
-    __device__ __forceinline__ uint32_t tree(uint16_t* probs) {
+    __device__ __forceinline__ uint32_t tree(uint16_t* probs, int nbits) {
         uint32_t m = 1;
-#pragma unroll
-        for (int i = 0; i < NBITS; i++) m = (m << 1) + bit(probs + m);
-        return m - (1u << NBITS);
+#pragma unroll 1
+        for (int i = 0; i < nbits; i++) m = (m << 1) + bit(probs + m);
+        return m - (1u << nbits);
     }
     // BitTreeDecoder.ReverseDecode (:27-37) / Decoder.ReverseDecode (Decoder.java:13-23)
     __device__ __forceinline__ uint32_t reverse(uint16_t* probs, int nbits) {
         uint32_t m = 1, symbol = 0;
+#pragma unroll 1
         for (int i = 0; i < nbits; i++) {
-            uint32_t b = bit(probs + m);
+            const uint32_t b = bit(probs + m);
             m = (m << 1) + b;
             symbol |= b << i;
         }
@@ -104,27 +107,36 @@ struct RangeDec {
     }
 };
 
-// LenDecoder.Decode (Decoder.java:48-59) on the pb-strided layout
+// LenDecoder.Decode (Decoder.java:48-59) on the pb-strided layout: one rolled tree loop
 __device__ __forceinline__ uint32_t decode_len(RangeDec& rd, uint16_t* lenp, int pb, uint32_t pos_state) {
-    if (rd.bit(lenp + 0) == 0) return rd.tree<kNumLowLenBits>(lenp + len_low(pb, pos_state));
-    if (rd.bit(lenp + 1) == 0) return kNumLowLenSymbols + rd.tree<kNumMidLenBits>(lenp + len_mid(pb, pos_state));
-    return kNumLowLenSymbols + kNumMidLenSymbols + rd.tree<kNumHighLenBits>(lenp + len_high(pb));
+    uint32_t base = 0, off = len_low(pb, pos_state);
+    int nbits = kNumLowLenBits;
+    if (rd.bit(lenp + 0)) {
+        if (rd.bit(lenp + 1)) {
+            base = kNumLowLenSymbols + kNumMidLenSymbols;
+            off = len_high(pb);
+            nbits = kNumHighLenBits;
+        } else {
+            base = kNumLowLenSymbols;
+            off = len_mid(pb, pos_state);
+        }
+    }
+    return base + rd.tree(lenp + off, nbits);
 }
 
-// LiteralDecoder.Decoder2.DecodeNormal / DecodeWithMatchByte (Decoder.java:70-95)
-template <typename P>
-__device__ __forceinline__ uint32_t decode_literal(RangeDec& rd, P* probs, bool matched, uint32_t match_byte) {
-    uint32_t symbol = 1;
-    if (matched) {
-        do {
-            uint32_t match_bit = (match_byte >> 7) & 1;
-            match_byte <<= 1;
-            uint32_t b = rd.bit(probs + ((1 + match_bit) << 8) + symbol);
-            symbol = (symbol << 1) | b;
-            if (match_bit != b) break;
-        } while (symbol < 0x100);
-    }
-    while (symbol < 0x100) symbol = (symbol << 1) | rd.bit(probs + symbol);
+// LiteralDecoder.Decoder2.DecodeNormal / DecodeWithMatchByte (Decoder.java:70-95) as one loop:
+// `offs` is 0x100 while the decoded bits still agree with the match byte (probability index
+// ((1 + matchBit) << 8) + symbol), 0 afterwards and for a plain literal (index symbol).
+__device__ __forceinline__ uint32_t decode_literal(RangeDec& rd, uint16_t* probs, bool matched, uint32_t match_byte) {
+    uint32_t symbol = 1, offs = matched ? 0x100u : 0u;
+#pragma unroll 1
+    do {
+        match_byte <<= 1;
+        const uint32_t mb = match_byte & offs;
+        const uint32_t b = rd.bit(probs + offs + mb + symbol);
+        symbol = (symbol << 1) | b;
+        offs &= b ? mb : ~mb;
+    } while (symbol < 0x100);
     return symbol & 0xFF;
 }
 
@@ -135,21 +147,23 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
     const uint64_t in_len = a.in_len[s];
     const uint8_t* in = a.in + a.in_off[s];
     uint8_t* out = a.out + a.out_off[s];
-    const uint64_t cap = a.out_cap[s];
+    const uint64_t cap64 = a.out_cap[s];
 
     // LzmaAlone.java:220-236 -- 5 property bytes + LE64 size; Decoder.java:303-318
     int status = 1;
-    uint64_t pos = 0;
+    uint32_t pos = 0;
     if (in_len < LZB_KERNEL_HEADER) {
         status = 0;  // "input .lzma file is too short" / "Can't read stream size"
+    } else if (in_len - LZB_KERNEL_HEADER >= 0xFFFFFFF0ull || cap64 >= 0xFFFFFFF0ull) {
+        status = LZB_KERNEL_E_UNSUPPORTED;  // positions are 32-bit in this kernel
     } else {
+        const uint32_t cap = (uint32_t)cap64;
         const uint32_t v = in[0];
         const int lc = v % 9, rem = v / 9, lp = rem % 5, pb = rem / 5;
         uint32_t dict = 0;
         uint64_t usize = 0;
         for (int i = 0; i < 4; i++) dict |= (uint32_t)in[1 + i] << (8 * i);
         for (int i = 0; i < 8; i++) usize |= (uint64_t)in[5 + i] << (8 * i);
-        const int64_t out_size = (int64_t)usize;
         // SetLcLpPb (:172-182) rejects pb > 4 (lc, lp are bounded by the
         // arithmetic); SetDictionarySize (:160-170) rejects a negative size.
         if (pb > 4 || (int32_t)dict < 0) {
@@ -163,32 +177,33 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
 
             const uint32_t dict_check = dict > 1 ? dict : 1;  // m_DictionarySizeCheck :166
             const uint32_t pos_mask = (1u << pb) - 1, lp_mask = (1u << lp) - 1;
-            const uint64_t limit = out_size < 0 ? ~0ull : (uint64_t)out_size;
+            // outSize < 0 decodes until the end marker; a size beyond the capacity ends in EV_CAPACITY
+            const uint32_t limit = usize > (uint64_t)cap ? 0xFFFFFFFFu : (uint32_t)usize;
 
             RangeDec rd;
             int state = 0;
             uint32_t rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0;
             uint32_t prev_byte = 0, match_byte = 0;
-            if (lane == 0) rd.init(in + LZB_KERNEL_HEADER, in + in_len);
+            if (lane == 0) rd.init(in + LZB_KERNEL_HEADER, (uint32_t)(in_len - LZB_KERNEL_HEADER));
 
             for (;;) {
-                int ev = EV_DONE;
-                uint32_t len = 0;
+                uint32_t evlen = EV_DONE;  // event | len << 2
                 if (lane == 0) {
+                    int ev = EV_DONE;
+                    uint32_t len = 0;
+#pragma unroll 1
                     while (pos < limit) {  // Decoder.Code :219
-                        const uint32_t pos_state = (uint32_t)pos & pos_mask;
+                        const uint32_t pos_state = pos & pos_mask;
                         if (rd.bit(model + L.is_match + (state << pb) + pos_state) == 0) {
-                            uint16_t* probs = lit + 0x300u * ((((uint32_t)pos & lp_mask) << lc) + (prev_byte >> (8 - lc)));
-                            prev_byte = decode_literal(rd, probs, !st_is_char(state), match_byte);
+                            uint16_t* probs = lit + 0x300u * (((pos & lp_mask) << lc) + (prev_byte >> (8 - lc)));
+                            prev_byte = decode_literal(rd, probs, state >= 7, match_byte);
                             if (pos >= cap) { ev = EV_CAPACITY; break; }
                             out[pos] = (uint8_t)prev_byte;
-                            // the byte the next matched literal would compare with (GetByte(rep0), :227)
-                            // is only needed in state >= 7, i.e. never directly after a literal
                             state = st_lit(state);
                             pos++;
                             continue;
                         }
-                        if (rd.bit(model + L.is_rep + state) == 1) {  // :233-259
+                        if (rd.bit(model + L.is_rep + state)) {  // :233-259
                             len = 0;
                             if (rd.bit(model + L.is_rep_g0 + state) == 0) {
                                 if (rd.bit(model + L.is_rep0_long + (state << pb) + pos_state) == 0) {
@@ -221,56 +236,67 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
                             rep1 = rep0;
                             len = kMatchMinLen + decode_len(rd, model + L.len, pb, pos_state);
                             state = st_match(state);
-                            const uint32_t pos_slot = rd.tree<kNumPosSlotBits>(model + L.pos_slot + (len_to_pos_state(len) << kNumPosSlotBits));
+                            const uint32_t pos_slot = rd.tree(model + L.pos_slot + (len_to_pos_state(len) << kNumPosSlotBits), kNumPosSlotBits);
                             if (pos_slot >= kStartPosModelIndex) {
                                 const int num_direct_bits = (int)(pos_slot >> 1) - 1;
                                 rep0 = (2 | (pos_slot & 1)) << num_direct_bits;
-                                if (pos_slot < kEndPosModelIndex) {
-                                    rep0 += rd.reverse(model + L.pos_dec + rep0 - pos_slot - 1, num_direct_bits);
-                                } else {
+                                uint16_t* rprobs = model + L.pos_dec + rep0 - pos_slot - 1;
+                                int rbits = num_direct_bits;
+                                if (pos_slot >= kEndPosModelIndex) {
                                     rep0 += rd.direct(num_direct_bits - kNumAlignBits) << kNumAlignBits;
-                                    rep0 += rd.reverse(model + L.pos_align, kNumAlignBits);
-                                    if ((int32_t)rep0 < 0) {
-                                        ev = (rep0 == 0xFFFFFFFFu) ? EV_DONE : EV_DATA_ERROR;  // end marker :277-282
-                                        break;
-                                    }
+                                    rprobs = model + L.pos_align;
+                                    rbits = kNumAlignBits;
+                                }
+                                rep0 += rd.reverse(rprobs, rbits);
+                                if (pos_slot >= kEndPosModelIndex && (int32_t)rep0 < 0) {
+                                    ev = (rep0 == 0xFFFFFFFFu) ? EV_DONE : EV_DATA_ERROR;  // end marker :277-282
+                                    break;
                                 }
                             } else {
                                 rep0 = pos_slot;
                             }
                         }
-                        if ((uint64_t)rep0 >= pos || rep0 >= dict_check) { ev = EV_DATA_ERROR; break; }  // :288-291
-                        if (pos + len > cap) { ev = EV_CAPACITY; break; }
+                        if (rep0 >= pos || rep0 >= dict_check) { ev = EV_DATA_ERROR; break; }  // :288-291
+                        if (len > cap - pos) { ev = EV_CAPACITY; break; }
                         ev = EV_MATCH;
                         break;
                     }
+                    evlen = (uint32_t)ev | (len << 2);
                 }
-                ev = __shfl_sync(kFull, ev, 0);
+                evlen = __shfl_sync(kFull, evlen, 0);
+                const int ev = (int)(evlen & 3);
                 if (ev != EV_MATCH) {
                     status = ev == EV_DONE ? 1 : (ev == EV_DATA_ERROR ? 0 : LZB_KERNEL_E_CAPACITY);
-                    pos = (uint64_t)__shfl_sync(kFull, (uint32_t)pos, 0) | ((uint64_t)__shfl_sync(kFull, (uint32_t)(pos >> 32), 0) << 32);
                     break;
                 }
-                // OutWindow.CopyBlock (OutWindow.java:53-67), all lanes.
-                len = __shfl_sync(kFull, len, 0);
+                // OutWindow.CopyBlock (OutWindow.java:53-67), all lanes: out[pos+k] = out[pos-d+(k mod d)].
+                const uint32_t len = evlen >> 2;
                 const uint32_t d = __shfl_sync(kFull, rep0, 0) + 1;
-                pos = (uint64_t)__shfl_sync(kFull, (uint32_t)pos, 0) | ((uint64_t)__shfl_sync(kFull, (uint32_t)(pos >> 32), 0) << 32);
-                __syncwarp();  // order lane 0's literal stores before the lanes' loads
+                pos = __shfl_sync(kFull, pos, 0);
+                __syncwarp();  // order earlier stores (lane 0's literals, other lanes' copies) before these loads
                 const uint8_t* src = out + pos - d;
                 uint8_t* dst = out + pos;
                 uint32_t last = 0, next = 0;
                 // index k = len is loaded but not stored: it is the byte GetByte(rep0) will
                 // return for a matched literal that follows (Decoder.java:227).
-                for (uint32_t k = lane; k <= len; k += 32) {
-                    const uint32_t b = src[k < d ? k : k % d];
-                    if (k < len) dst[k] = (uint8_t)b;
-                    if (k == len - 1) last = b;
-                    if (k == len) next = b;
+                if (d > len) {
+                    for (uint32_t k = lane; k <= len; k += 32) {
+                        const uint32_t b = src[k];
+                        if (k < len) dst[k] = (uint8_t)b;
+                        if (k == len - 1) last = b;
+                        if (k == len) next = b;
+                    }
+                } else {
+                    for (uint32_t k = lane; k <= len; k += 32) {
+                        const uint32_t b = src[k % d];
+                        if (k < len) dst[k] = (uint8_t)b;
+                        if (k == len - 1) last = b;
+                        if (k == len) next = b;
+                    }
                 }
                 prev_byte = __shfl_sync(kFull, last, (len - 1) & 31);  // GetByte(0) :294
                 match_byte = __shfl_sync(kFull, next, len & 31);
                 pos += len;
-                __syncwarp();
             }
         }
     }

@@ -8,6 +8,7 @@
 
 #define LZB_KERNEL_HEADER 13
 #define LZB_KERNEL_E_CAPACITY (-4)
+#define LZB_KERNEL_E_UNSUPPORTED (-5)
 
 namespace lzb {
 
