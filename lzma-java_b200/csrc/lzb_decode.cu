@@ -24,11 +24,11 @@ namespace lzb {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
-// Range decoder state of one stream, in lane 0's registers.  Every bit goes
-// through ONE code path (`bit`), and every multi-bit symbol through a rolled
-// loop around it, so that the whole kernel stays a few hundred instructions:
-// 15 warps per SM execute different parts of it at any time and the
-// instruction caches hold 32 KB.
+// Range decoder state of one stream, in lane 0's registers.  The kernel is
+// issue-bound (profiles/: ~75 % of issue slots busy with 15 streams per SM), so
+// the one thing that matters is the instruction count of a bit decode.  `bit_s`
+// is written in PTX against a shared-memory byte address: 13 instructions
+// (LDS, SHF, IMAD, ISETP, IADD, SEL, @IADD, SEL, IADD, SHF, IADD, STS, SEL).
 struct RangeDec {
     uint32_t range, code, nextb, ip, len;
     const uint8_t* in;
@@ -60,10 +60,41 @@ struct RangeDec {
             fetch();
         }
     }
-    // RangeDecoder.DecodeBit (:43-64), branch-free:
+    // RangeDecoder.DecodeBit (:43-64) on a shared-memory probability, branch-free:
     //   bit 0: p += (2048 - p) >> 5      bit 1: p -= p >> 5
     // are both  p -= (p - k) >> 5 (arithmetic shift) with k = 2017 (= 2048 - 31) resp. 0.
-    __device__ __forceinline__ uint32_t bit(uint16_t* prob) {
+    __device__ __forceinline__ uint32_t bit_s(uint32_t saddr) {
+        uint32_t b;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred z;\n\t"
+            ".reg .u16 ph;\n\t"
+            ".reg .u32 p, t, bound, r1, k;\n\t"
+            ".reg .s32 d;\n\t"
+            "ld.shared.u16 ph, [%3];\n\t"
+            "cvt.u32.u16 p, ph;\n\t"
+            "shr.u32 t, %0, 11;\n\t"
+            "mul.lo.u32 bound, t, p;\n\t"
+            "setp.lt.u32 z, %1, bound;\n\t"
+            "sub.u32 r1, %0, bound;\n\t"
+            "selp.u32 %0, bound, r1, z;\n\t"
+            "@!z sub.u32 %1, %1, bound;\n\t"
+            "selp.u32 k, 2017, 0, z;\n\t"
+            "sub.s32 d, p, k;\n\t"
+            "shr.s32 d, d, 5;\n\t"
+            "sub.u32 p, p, d;\n\t"
+            "cvt.u16.u32 ph, p;\n\t"
+            "st.shared.u16 [%3], ph;\n\t"
+            "selp.u32 %2, 0, 1, z;\n\t"
+            "}"
+            : "+r"(range), "+r"(code), "=r"(b)
+            : "r"(saddr)
+            : "memory");
+        normalize();
+        return b;
+    }
+    // the same on a generic pointer (literal coders spilled to global memory)
+    __device__ __forceinline__ uint32_t bit_g(uint16_t* prob) {
         const uint32_t p0 = *prob;
         const uint32_t bound = (range >> kNumBitModelTotalBits) * p0;
         const bool one = code >= bound;
@@ -87,53 +118,69 @@ struct RangeDec {
         }
         return result;
     }
-    // BitTreeDecoder.Decode (BitTreeDecoder.java:19-25)
-    __device__ __forceinline__ uint32_t tree(uint16_t* probs, int nbits) {
-        uint32_t m = 1;
+    // BitTreeDecoder.Decode (BitTreeDecoder.java:19-25); `m2` walks the tree as a byte offset (2 * m)
+    template <int NBITS>
+    __device__ __forceinline__ uint32_t tree(uint32_t sbase) {
+        uint32_t m2 = 2;
+#pragma unroll
+        for (int i = 0; i < NBITS; i++) m2 = (m2 << 1) + (bit_s(sbase + m2) << 1);
+        return (m2 >> 1) - (1u << NBITS);
+    }
+    __device__ __forceinline__ uint32_t tree_n(uint32_t sbase, int nbits) {
+        uint32_t m2 = 2;
 #pragma unroll 1
-        for (int i = 0; i < nbits; i++) m = (m << 1) + bit(probs + m);
-        return m - (1u << nbits);
+        for (int i = 0; i < nbits; i++) m2 = (m2 << 1) + (bit_s(sbase + m2) << 1);
+        return (m2 >> 1) - (1u << nbits);
     }
     // BitTreeDecoder.ReverseDecode (:27-37) / Decoder.ReverseDecode (Decoder.java:13-23)
-    __device__ __forceinline__ uint32_t reverse(uint16_t* probs, int nbits) {
-        uint32_t m = 1, symbol = 0;
+    __device__ __forceinline__ uint32_t reverse(uint32_t sbase, int nbits) {
+        uint32_t m2 = 2, symbol = 0;
 #pragma unroll 1
         for (int i = 0; i < nbits; i++) {
-            const uint32_t b = bit(probs + m);
-            m = (m << 1) + b;
+            const uint32_t b = bit_s(sbase + m2);
+            m2 = (m2 << 1) + (b << 1);
             symbol |= b << i;
         }
         return symbol;
     }
 };
 
-// LenDecoder.Decode (Decoder.java:48-59) on the pb-strided layout: one rolled tree loop
-__device__ __forceinline__ uint32_t decode_len(RangeDec& rd, uint16_t* lenp, int pb, uint32_t pos_state) {
-    uint32_t base = 0, off = len_low(pb, pos_state);
-    int nbits = kNumLowLenBits;
-    if (rd.bit(lenp + 0)) {
-        if (rd.bit(lenp + 1)) {
-            base = kNumLowLenSymbols + kNumMidLenSymbols;
-            off = len_high(pb);
-            nbits = kNumHighLenBits;
-        } else {
-            base = kNumLowLenSymbols;
-            off = len_mid(pb, pos_state);
-        }
-    }
-    return base + rd.tree(lenp + off, nbits);
+// LenDecoder.Decode (Decoder.java:48-59) on the pb-strided layout; `slen` = shared address of the coder
+__device__ __forceinline__ uint32_t decode_len(RangeDec& rd, uint32_t slen, int pb, uint32_t pos_state) {
+    if (rd.bit_s(slen) == 0) return rd.tree<kNumLowLenBits>(slen + 2 * len_low(pb, pos_state));
+    if (rd.bit_s(slen + 2) == 0) return kNumLowLenSymbols + rd.tree<kNumMidLenBits>(slen + 2 * len_mid(pb, pos_state));
+    return kNumLowLenSymbols + kNumMidLenSymbols + rd.tree_n(slen + 2 * len_high(pb), kNumHighLenBits);
 }
 
-// LiteralDecoder.Decoder2.DecodeNormal / DecodeWithMatchByte (Decoder.java:70-95) as one loop:
-// `offs` is 0x100 while the decoded bits still agree with the match byte (probability index
-// ((1 + matchBit) << 8) + symbol), 0 afterwards and for a plain literal (index symbol).
-__device__ __forceinline__ uint32_t decode_literal(RangeDec& rd, uint16_t* probs, bool matched, uint32_t match_byte) {
+// LiteralDecoder.Decoder2.DecodeNormal (Decoder.java:70-77), unrolled
+__device__ __forceinline__ uint32_t decode_literal_s(RangeDec& rd, uint32_t sprobs) {
+    uint32_t m2 = 2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) m2 = (m2 << 1) + (rd.bit_s(sprobs + m2) << 1);
+    return (m2 >> 1) & 0xFF;
+}
+// DecodeWithMatchByte (Decoder.java:79-95): `offs` is 0x100 while the decoded bits still agree
+// with the match byte (probability index ((1 + matchBit) << 8) + symbol), 0 afterwards.
+__device__ __forceinline__ uint32_t decode_literal_matched_s(RangeDec& rd, uint32_t sprobs, uint32_t match_byte) {
+    uint32_t symbol = 1, offs = 0x100u;
+#pragma unroll 1
+    do {
+        match_byte <<= 1;
+        const uint32_t mb = match_byte & offs;
+        const uint32_t b = rd.bit_s(sprobs + 2 * (offs + mb + symbol));
+        symbol = (symbol << 1) | b;
+        offs &= b ? mb : ~mb;
+    } while (symbol < 0x100);
+    return symbol & 0xFF;
+}
+// both forms on a generic pointer
+__device__ __forceinline__ uint32_t decode_literal_g(RangeDec& rd, uint16_t* probs, bool matched, uint32_t match_byte) {
     uint32_t symbol = 1, offs = matched ? 0x100u : 0u;
 #pragma unroll 1
     do {
         match_byte <<= 1;
         const uint32_t mb = match_byte & offs;
-        const uint32_t b = rd.bit(probs + offs + mb + symbol);
+        const uint32_t b = rd.bit_g(probs + offs + mb + symbol);
         symbol = (symbol << 1) | b;
         offs &= b ? mb : ~mb;
     } while (symbol < 0x100);
@@ -181,6 +228,7 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
             const uint32_t limit = usize > (uint64_t)cap ? 0xFFFFFFFFu : (uint32_t)usize;
 
             RangeDec rd;
+            const uint32_t sm = (uint32_t)__cvta_generic_to_shared(model);  // shared byte address of the model
             int state = 0;
             uint32_t rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0;
             uint32_t prev_byte = 0, match_byte = 0;
@@ -194,28 +242,34 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
 #pragma unroll 1
                     while (pos < limit) {  // Decoder.Code :219
                         const uint32_t pos_state = pos & pos_mask;
-                        if (rd.bit(model + L.is_match + (state << pb) + pos_state) == 0) {
-                            uint16_t* probs = lit + 0x300u * (((pos & lp_mask) << lc) + (prev_byte >> (8 - lc)));
-                            prev_byte = decode_literal(rd, probs, state >= 7, match_byte);
+                        if (rd.bit_s(sm + 2 * (L.is_match + (state << pb) + pos_state)) == 0) {
+                            const uint32_t coder = 0x300u * (((pos & lp_mask) << lc) + (prev_byte >> (8 - lc)));
+                            if (LIT_SMEM) {
+                                const uint32_t sprobs = sm + 2 * (L.literal + coder);
+                                prev_byte = state >= 7 ? decode_literal_matched_s(rd, sprobs, match_byte) : decode_literal_s(rd, sprobs);
+                            } else {
+                                prev_byte = decode_literal_g(rd, lit_global + coder, state >= 7, match_byte);
+                            }
                             if (pos >= cap) { ev = EV_CAPACITY; break; }
                             out[pos] = (uint8_t)prev_byte;
                             state = st_lit(state);
                             pos++;
                             continue;
                         }
-                        if (rd.bit(model + L.is_rep + state)) {  // :233-259
-                            len = 0;
-                            if (rd.bit(model + L.is_rep_g0 + state) == 0) {
-                                if (rd.bit(model + L.is_rep0_long + (state << pb) + pos_state) == 0) {
+                        const uint32_t is_rep = rd.bit_s(sm + 2 * (L.is_rep + state));
+                        len = 0;
+                        if (is_rep) {  // :233-259
+                            if (rd.bit_s(sm + 2 * (L.is_rep_g0 + state)) == 0) {
+                                if (rd.bit_s(sm + 2 * (L.is_rep0_long + (state << pb) + pos_state)) == 0) {
                                     state = st_shortrep(state);
                                     len = 1;
                                 }
                             } else {
                                 uint32_t distance;
-                                if (rd.bit(model + L.is_rep_g1 + state) == 0) {
+                                if (rd.bit_s(sm + 2 * (L.is_rep_g1 + state)) == 0) {
                                     distance = rep1;
                                 } else {
-                                    if (rd.bit(model + L.is_rep_g2 + state) == 0) {
+                                    if (rd.bit_s(sm + 2 * (L.is_rep_g2 + state)) == 0) {
                                         distance = rep2;
                                     } else {
                                         distance = rep3;
@@ -226,25 +280,24 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
                                 rep1 = rep0;
                                 rep0 = distance;
                             }
-                            if (len == 0) {
-                                len = decode_len(rd, model + L.rep_len, pb, pos_state) + kMatchMinLen;
-                                state = st_longrep(state);
-                            }
-                        } else {  // :260-286
+                        }
+                        if (len == 0) {  // one length decoder site for both coders (:255-258, :264)
+                            len = kMatchMinLen + decode_len(rd, sm + 2 * (is_rep ? L.rep_len : L.len), pb, pos_state);
+                            state = is_rep ? st_longrep(state) : st_match(state);
+                        }
+                        if (!is_rep) {  // :260-286
                             rep3 = rep2;
                             rep2 = rep1;
                             rep1 = rep0;
-                            len = kMatchMinLen + decode_len(rd, model + L.len, pb, pos_state);
-                            state = st_match(state);
-                            const uint32_t pos_slot = rd.tree(model + L.pos_slot + (len_to_pos_state(len) << kNumPosSlotBits), kNumPosSlotBits);
+                            const uint32_t pos_slot = rd.tree<kNumPosSlotBits>(sm + 2 * (L.pos_slot + (len_to_pos_state(len) << kNumPosSlotBits)));
                             if (pos_slot >= kStartPosModelIndex) {
                                 const int num_direct_bits = (int)(pos_slot >> 1) - 1;
                                 rep0 = (2 | (pos_slot & 1)) << num_direct_bits;
-                                uint16_t* rprobs = model + L.pos_dec + rep0 - pos_slot - 1;
+                                uint32_t rprobs = sm + 2 * (L.pos_dec + rep0 - pos_slot - 1);
                                 int rbits = num_direct_bits;
                                 if (pos_slot >= kEndPosModelIndex) {
                                     rep0 += rd.direct(num_direct_bits - kNumAlignBits) << kNumAlignBits;
-                                    rprobs = model + L.pos_align;
+                                    rprobs = sm + 2 * L.pos_align;
                                     rbits = kNumAlignBits;
                                 }
                                 rep0 += rd.reverse(rprobs, rbits);
