@@ -61,7 +61,8 @@ size_t carve(uint8_t* base, uint32_t wb, uint32_t np, uint32_t hash_stride, uint
     uint32_t* prev3 = c.take<uint32_t>((size_t)wb * np);
     uint32_t* son = c.take<uint32_t>((size_t)wb * 2 * np);
     uint32_t* idx = c.take<uint32_t>((size_t)wb * np);
-    uint32_t* pairs = c.take<uint32_t>((size_t)wb * pair_cap);
+    uint32_t* pairs = c.take<uint32_t>((size_t)wb * pair_cap + 64);   // + slack: the parser prefetches 32 slots blindly
+    uint16_t* pairs2 = c.take<uint16_t>((size_t)wb * pair_cap + 64);
     void* opt = c.take<uint8_t>(slots * parse_opt_bytes_per_slot());
     uint16_t* lit = c.take<uint16_t>(lit_slots);
     if (w) {
@@ -72,6 +73,7 @@ size_t carve(uint8_t* base, uint32_t wb, uint32_t np, uint32_t hash_stride, uint
         w->son = son;
         w->idx = idx;
         w->pairs = pairs;
+        w->pairs2 = pairs2;
         w->pair_used = pair_used;
         w->overflow = ctl + 1;
     }

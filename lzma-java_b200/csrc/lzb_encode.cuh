@@ -51,6 +51,8 @@ struct MfWave {
     uint32_t* son;           // [n_blocks][2*np]         absolute-indexed tree links
     uint32_t* idx;           // [n_blocks][np]           offset of the position's list in `pairs` or kMfEmpty
     uint32_t* pairs;         // [n_blocks][pair_cap]     lists: count, then count packed pairs
+    uint16_t* pairs2;        // [n_blocks][pair_cap]     per pair: GetMatchLen(len, dist, fb) after "match + literal"
+                             //                          (Encoder.java:769), a function of the data only
     uint32_t* pair_used;     // [n_blocks]               zeroed; bump allocator
     uint32_t* overflow;      // [1]                      zeroed; set when a block ran out of pair slots
 };

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(256) lzb_mf_tree_kernel(MfWave w) {
     uint32_t* son = w.son + (size_t)b * 2 * w.np;
     uint32_t* idx = w.idx + (size_t)b * w.np;
     uint32_t* pairs_out = w.pairs + (size_t)b * w.pair_cap;
+    uint16_t* pairs2_out = w.pairs2 + (size_t)b * w.pair_cap;
     const uint32_t direct = w.bt4 ? 0 : 2;  // kNumHashDirectBytes
 
     uint32_t pairs[kMatchMaxLen];
@@ -194,7 +195,20 @@ __global__ void __launch_bounds__(256) lzb_mf_tree_kernel(MfWave w) {
             if (off + cnt + 1 <= w.pair_cap) {
                 where = off;
                 pairs_out[off] = cnt;
-                for (uint32_t i = 0; i < cnt; i++) pairs_out[off + 1 + i] = pairs[i];
+                for (uint32_t i = 0; i < cnt; i++) {
+                    pairs_out[off + 1 + i] = pairs[i];
+                    // length of the rep0 match that could follow "this match + one literal"
+                    // (Encoder.java:766-770 asks for it at every pair boundary)
+                    const uint32_t len = pairs[i] >> kPairDistBits, dist = pairs[i] & kPairDistMask;
+                    const uint32_t s1 = pos1 + len + 1;  // 1-based start of the continuation
+                    uint32_t lim = s1 <= n ? n + 1 - s1 : 0;
+                    if (lim > (uint32_t)w.fb) lim = (uint32_t)w.fb;
+                    const uint8_t* a = buf + s1;
+                    const uint8_t* b = a - dist - 1;
+                    uint32_t k = 0;
+                    while (k < lim && a[k] == b[k]) k++;
+                    pairs2_out[off + 1 + i] = (uint16_t)k;
+                }
             } else {
                 *w.overflow = 1;
             }

@@ -85,7 +85,12 @@ __device__ __forceinline__ int ln_state(uint32_t l) { return (int)((l >> 24) & 0
 __device__ __forceinline__ bool ln_prev1(uint32_t l) { return (l >> 28) & 1; }
 __device__ __forceinline__ bool ln_prev2(uint32_t l) { return (l >> 29) & 1; }
 
-// ---- range encoder (RangeEncoder.java:23-87); lives in lane 0 ---------------
+// ---- range encoder (RangeEncoder.java:23-87) --------------------------------
+// The coder state is replicated in every lane (control flow stays uniform); only lane 0
+// stores output bytes.  A symbol is emitted as a batch: lane k prepares the k-th binary
+// decision (probability address + bit, or a direct bit), adapts its own probability --
+// all addresses of one symbol are distinct -- and the batch loop then folds the
+// decisions into low/range in order, fetching each (old probability, bit) by shuffle.
 struct RangeEnc {
     uint64_t low;
     uint32_t range;
@@ -93,8 +98,9 @@ struct RangeEnc {
     uint32_t cache;
     uint8_t* out;
     uint64_t pos, cap;
+    int lane;
 
-    __device__ __forceinline__ void init(uint8_t* o, uint64_t c) {
+    __device__ __forceinline__ void init(uint8_t* o, uint64_t c, int l) {
         low = 0;
         range = 0xFFFFFFFFu;
         cache_size = 1;
@@ -102,17 +108,16 @@ struct RangeEnc {
         out = o;
         pos = 0;
         cap = c;
+        lane = l;
     }
-    __device__ __forceinline__ void put(uint32_t b) {
-        if (pos < cap) out[pos] = (uint8_t)b;
-        pos++;
-    }
-    __device__ __noinline__ void shift_low() {
+    __device__ __noinline__ static void shift_low_impl(uint64_t& low, uint32_t& cache_size, uint32_t& cache, uint8_t* out,
+                                                       uint64_t& pos, uint64_t cap, int lane) {  // :73-87
         const uint32_t low_hi = (uint32_t)(low >> 32);
         if (low_hi != 0 || low < 0xFF000000ull) {
             uint32_t temp = cache;
             do {
-                put(temp + low_hi);
+                if (lane == 0 && pos < cap) out[pos] = (uint8_t)(temp + low_hi);
+                pos++;
                 temp = 0xFF;
             } while (--cache_size != 0);
             cache = ((uint32_t)low) >> 24;
@@ -120,53 +125,41 @@ struct RangeEnc {
         cache_size++;
         low = (low & 0xFFFFFF) << 8;
     }
-    __device__ __forceinline__ void encode(uint16_t* prob, uint32_t bit) {
-        const uint32_t p = *prob;
-        const uint32_t bound = (range >> kNumBitModelTotalBits) * p;
-        if (bit == 0) {
-            range = bound;
-            *prob = (uint16_t)(p + ((kBitModelTotal - p) >> kNumMoveBits));
-        } else {
-            low += bound;
-            range -= bound;
-            *prob = (uint16_t)(p - (p >> kNumMoveBits));
-        }
-        if (range < kTopValue) {
-            range <<= 8;
-            shift_low();
-        }
+    __device__ __forceinline__ void shift_low() { shift_low_impl(low, cache_size, cache, out, pos, cap, lane); }
+    __device__ __forceinline__ void flush() {  // :31-36
+#pragma unroll 1
+        for (int i = 0; i < 5; i++) shift_low();
     }
-    __device__ __forceinline__ void direct(uint32_t v, int nbits) {
-        for (int i = nbits - 1; i >= 0; i--) {
-            range >>= 1;
-            if ((v >> i) & 1) low += range;
+    // Encode `cnt` (<= 32) decisions.  Lane k < cnt passes its decision: `prob` (ignored for a
+    // direct bit), `bit`, `direct`.  RangeEncoder.encode :38-54 / encodeDirectBits :56-67.
+    __device__ __forceinline__ void batch(int cnt, uint16_t* prob, uint32_t bit, bool direct) {
+        uint32_t p = 0;
+        if (lane < cnt && !direct) {
+            p = *prob;
+            *prob = (uint16_t)(bit ? p - (p >> kNumMoveBits) : p + ((kBitModelTotal - p) >> kNumMoveBits));
+        }
+        const uint32_t w = p | (bit << 16) | ((uint32_t)direct << 17);
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {
+            const uint32_t e = __shfl_sync(kFull, w, k);
+            if (e & 0x20000u) {
+                range >>= 1;
+                if (e & 0x10000u) low += range;
+            } else {
+                const uint32_t bound = (range >> kNumBitModelTotalBits) * (e & 0xFFFFu);
+                if (e & 0x10000u) {
+                    low += bound;
+                    range -= bound;
+                } else {
+                    range = bound;
+                }
+            }
             if (range < kTopValue) {
                 range <<= 8;
                 shift_low();
             }
         }
-    }
-    __device__ __forceinline__ void flush() {
-        for (int i = 0; i < 5; i++) shift_low();
-    }
-    // BitTreeEncoder.encode / ReverseEncode (BitTreeEncoder.java:18-36, Encoder.java:196-205)
-    __device__ __forceinline__ void tree(uint16_t* probs, int nbits, uint32_t symbol) {
-        uint32_t m = 1;
-        for (int bi = nbits; bi != 0;) {
-            bi--;
-            const uint32_t bit = (symbol >> bi) & 1;
-            encode(probs + m, bit);
-            m = (m << 1) | bit;
-        }
-    }
-    __device__ __forceinline__ void reverse(uint16_t* probs, int nbits, uint32_t symbol) {
-        uint32_t m = 1;
-        for (int i = 0; i < nbits; i++) {
-            const uint32_t bit = symbol & 1;
-            encode(probs + m, bit);
-            m = (m << 1) | bit;
-            symbol >>= 1;
-        }
+        __syncwarp();
     }
 };
 
@@ -179,8 +172,8 @@ struct SliceLayout {
 __host__ __device__ inline SliceLayout make_slice(int lc, int lp, int pb, int fb, uint32_t budget) {
     const ModelLayout L = make_layout(lc, lp, pb);
     const uint32_t table = (uint32_t)(fb - 1);
-    uint32_t ring_nodes = 256;
-    while (ring_nodes < (uint32_t)(4 * fb + 3)) ring_nodes <<= 1;
+    // a DP step touches nodes [cur - 2fb - 1, cur + 2fb + 1]
+    const uint32_t ring_nodes = ((uint32_t)(4 * fb + 3) + 31) & ~31u;
     SliceLayout s;
     for (int with_lit = 1; with_lit >= 0; with_lit--) {
         uint32_t o = (uint32_t)(L.n_fixed + (with_lit ? L.n_literal : 0)) * 2;
@@ -202,6 +195,28 @@ __host__ __device__ inline SliceLayout make_slice(int lc, int lp, int pb, int fb
     return s;
 }
 
+// InWindow.GetMatchLen (InWindow.java:120-134) from absolute position `s`, 32 bytes per round;
+// every lane returns the same value.  Out of line: it is the rare continuation of a bitmap run.
+__device__ __noinline__ int warp_match_len(const uint8_t* data, uint32_t n, int lane, uint32_t s, uint32_t distance, int limit) {
+    if (limit > 0 && s + (uint32_t)limit > n) limit = (int)(n - s);
+    const uint8_t* a = data + s;
+    const uint8_t* b = a - distance - 1;
+    int len = 0;
+    while (len < limit) {
+        const int i = len + lane;
+        const bool ok = i < limit;
+        uint32_t x = 0, y = 1;
+        if (ok) {
+            x = a[i];
+            y = b[i];
+        }
+        const unsigned neq = __ballot_sync(kFull, x != y);
+        if (neq) return len + (__ffs(neq) - 1);
+        len += 32;
+    }
+    return limit > 0 ? limit : 0;
+}
+
 // ---- everything one stream needs (identical in every lane unless noted) -----
 struct Enc {
     const CtaTables* T;
@@ -217,7 +232,7 @@ struct Enc {
     OptNode* ring;          // [R] shared
     OptNode* gopt;          // [kNumOpts] global spill
     OptNode* qbase;         // where Backward left the decision queue (ring or gopt)
-    uint32_t rmask;
+    uint32_t rsize, rinv;   // ring size (a multiple of 32) and ceil(2^24 / rsize)
     ModelLayout L;
     const uint8_t* data;
     uint32_t n;
@@ -229,7 +244,9 @@ struct Enc {
     bool eos;
     RangeEnc rc;            // meaningful in lane 0 only
     uint32_t m;             // match-finder cursor, 0-based (== _pos - 1 of the reference's InWindow)
-    uint32_t pre_pos, pre_off;  // prefetched idx[] entry
+    const uint16_t* pairs2;
+    uint32_t pf_pos, pf_cnt, pf_pair, pf_l2, pf_from;  // prefetched list (pf_pair / pf_l2 differ per lane)
+    uint32_t pf_off_pos, pf_off;                        // prefetched idx[] entry
     int state;
     uint32_t prev_byte;
     uint32_t rep_dist[4];
@@ -289,31 +306,17 @@ struct Enc {
         return lit + 0x300u * (((pos & lp_mask) << lc) + (prev >> (8 - lc)));
     }
 
-    __device__ __forceinline__ OptNode* node(int i) const { return ring + ((uint32_t)i & rmask); }
+    // i mod rsize for i < 4096: the 2^24 reciprocal is exact in that range (rsize >= 128)
+    __device__ __forceinline__ uint32_t slot(uint32_t i) const { return i - ((i * rinv) >> 24) * rsize; }
+    __device__ __forceinline__ OptNode* node(int i) const { return ring + slot((uint32_t)i); }
 
     // ---- window (InWindow.java:115-138, whole block resident) ----
     __device__ __forceinline__ uint32_t byte_at(int index) const { return data[m + index]; }
     __device__ __forceinline__ int avail() const { return (int)(n - m); }
 
     // GetMatchLen for an absolute start `s`, 32 bytes per round (all lanes, uniform result)
-    __device__ int match_len_abs(uint32_t s, uint32_t distance, int limit) const {
-        if (limit > 0 && s + (uint32_t)limit > n) limit = (int)(n - s);
-        const uint8_t* a = data + s;
-        const uint8_t* b = a - distance - 1;
-        int len = 0;
-        while (len < limit) {
-            const int i = len + lane;
-            const bool ok = i < limit;
-            uint32_t x = 0, y = 1;
-            if (ok) {
-                x = a[i];
-                y = b[i];
-            }
-            const unsigned neq = __ballot_sync(kFull, x != y);
-            if (neq) return len + (__ffs(neq) - 1);
-            len += 32;
-        }
-        return limit > 0 ? limit : 0;
+    __device__ __forceinline__ int match_len_abs(uint32_t s, uint32_t distance, int limit) const {
+        return warp_match_len(data, n, lane, s, distance, limit);
     }
 
     // run of set bits in a 32-byte equality bitmap starting at bit `start`, continued in memory
@@ -332,21 +335,43 @@ struct Enc {
     __device__ __forceinline__ int md_len(int i) const { return (int)(md[i] >> kPairDistBits); }
     __device__ __forceinline__ uint32_t md_dist(int i) const { return md[i] & kPairDistMask; }
 
+    // List of 0-based position p: idx[p + 1] -> pairs[off] = count, pairs[off + 1 ..] = pairs.
+    // The lists are read one step ahead into registers (lane i holds pair i), and idx[] two steps
+    // ahead, so that a DP step never waits for global memory on the list.
+    __device__ __forceinline__ void prefetch_list(uint32_t p) {  // p = position whose list to fetch
+        pf_pos = p;
+        pf_cnt = 0;
+        pf_pair = 0;
+        pf_l2 = 0;
+        uint32_t off = kMfEmpty;
+        if (p < n) off = (pf_off_pos == p) ? pf_off : idx[p + 1];
+        if (off != kMfEmpty) {
+            pf_cnt = pairs[off];
+            pf_pair = pairs[off + 1 + lane];   // blind: lanes >= count read slack
+            pf_l2 = pairs2[off + 1 + lane];
+        }
+        pf_from = off;
+        pf_off_pos = p + 1;
+        pf_off = kMfEmpty;
+        if (p + 1 < n) pf_off = idx[p + 2];
+    }
+
     __device__ int read_match_distances() {  // Encoder.java:275-287
         __syncwarp();  // everyone is done with the previous list
-        const uint32_t off = (pre_pos == m + 1) ? pre_off : idx[m + 1];
-        int cnt = 0;
-        if (off != kMfEmpty) {
-            cnt = (int)pairs[off];
-            for (int i = lane; i < cnt; i += 32) md[i] = pairs[off + 1 + i];
+        if (pf_pos != m) prefetch_list(m);
+        const int cnt = (int)pf_cnt;
+        if (lane < cnt) {
+            md[lane] = pf_pair;
+            md2[lane] = (uint16_t)pf_l2;
+        }
+        for (int i = 32 + lane; i < cnt; i += 32) {
+            md[i] = pairs[pf_from + 1 + i];
+            md2[i] = pairs2[pf_from + 1 + i];
         }
         __syncwarp();
         num_pairs = cnt;
         m++;  // fillMatches advanced the window
-        if (m < n) {  // prefetch the next position's list head
-            pre_pos = m + 1;
-            pre_off = idx[m + 1];
-        }
+        prefetch_list(m);
         int length = 0;
         if (cnt > 0) {
             length = md_len(cnt - 1);
@@ -383,23 +408,6 @@ struct Enc {
         if (lane == 0) len_counters[which * 16 + ps] = table_size;
         __syncwarp();
     }
-    // lane 0: LenEncoder.encode :33-48
-    __device__ void len_encode_bits(int which, uint32_t symbol, uint32_t ps) {
-        uint16_t* lp_ = model + (which ? L.rep_len : L.len);
-        if (symbol < kNumLowLenSymbols) {
-            rc.encode(lp_ + 0, 0);
-            rc.tree(lp_ + len_low(pb, ps), kNumLowLenBits, symbol);
-        } else {
-            rc.encode(lp_ + 0, 1);
-            if (symbol < kNumLowLenSymbols + kNumMidLenSymbols) {
-                rc.encode(lp_ + 1, 0);
-                rc.tree(lp_ + len_mid(pb, ps), kNumMidLenBits, symbol - kNumLowLenSymbols);
-            } else {
-                rc.encode(lp_ + 1, 1);
-                rc.tree(lp_ + len_high(pb), kNumHighLenBits, symbol - kNumLowLenSymbols - kNumMidLenSymbols);
-            }
-        }
-    }
     // all lanes, after the bits were emitted: LenPriceTableEncoder.encode :32-37
     __device__ void len_count(int which, uint32_t ps) {
         const int c = len_counters[which * 16 + ps] - 1;
@@ -413,29 +421,50 @@ struct Enc {
     }
 
     // ---- literal coder (LiteralEncoder.java:17-64) ----
-    __device__ void lit_encode(uint16_t* probs, uint32_t symbol) {  // lane 0
-        uint32_t context = 1;
-        for (int i = 7; i >= 0; i--) {
-            const uint32_t bit = (symbol >> i) & 1;
-            rc.encode(probs + context, bit);
-            context = (context << 1) | bit;
-        }
+    // ---- decision lists: lane `j` of a group describes one binary decision of the symbol ----
+    // MSB-first bit tree of `nbits` (BitTreeEncoder.encode :18-26): decision j codes bit nbits-1-j at node m_j
+    __device__ __forceinline__ void tree_decision(int j, uint16_t* probs, int nbits, uint32_t symbol, uint16_t*& ptr, uint32_t& bit) const {
+        ptr = probs + ((1u << j) | (symbol >> (nbits - j)));
+        bit = (symbol >> (nbits - 1 - j)) & 1;
     }
-    __device__ void lit_encode_matched(uint16_t* probs, uint32_t match_byte, uint32_t symbol) {  // lane 0
-        uint32_t context = 1;
-        bool same = true;
-        for (int i = 7; i >= 0; i--) {
-            const uint32_t bit = (symbol >> i) & 1;
-            uint32_t st = context;
-            if (same) {
-                const uint32_t match_bit = (match_byte >> i) & 1;
-                st += (1 + match_bit) << 8;
-                same = (match_bit == bit);
-            }
-            rc.encode(probs + st, bit);
-            context = (context << 1) | bit;
-        }
+    // LSB-first bit tree (ReverseEncode :28-36, Encoder.java:196-205)
+    __device__ __forceinline__ void reverse_decision(int j, uint16_t* probs, uint32_t symbol, uint16_t*& ptr, uint32_t& bit) const {
+        ptr = probs + ((1u << j) | (j ? __brev(symbol) >> (32 - j) : 0u));
+        bit = (symbol >> j) & 1;
     }
+    // LenEncoder.encode (:33-48): returns the number of decisions; lane offset j within the symbol
+    __device__ __forceinline__ int len_decisions(int j, int which, uint32_t symbol, uint32_t ps, uint16_t*& ptr, uint32_t& bit) const {
+        uint16_t* lp_ = model + (which ? L.rep_len : L.len);
+        int nchoice, nbits;
+        uint16_t* tree;
+        uint32_t sym;
+        if (symbol < kNumLowLenSymbols) {
+            nchoice = 1; nbits = kNumLowLenBits; tree = lp_ + len_low(pb, ps); sym = symbol;
+        } else if (symbol < kNumLowLenSymbols + kNumMidLenSymbols) {
+            nchoice = 2; nbits = kNumMidLenBits; tree = lp_ + len_mid(pb, ps); sym = symbol - kNumLowLenSymbols;
+        } else {
+            nchoice = 2; nbits = kNumHighLenBits; tree = lp_ + len_high(pb); sym = symbol - kNumLowLenSymbols - kNumMidLenSymbols;
+        }
+        if (j < 0) {
+            // a lane that belongs to an earlier part of the symbol
+        } else if (j < nchoice) {
+            ptr = lp_ + j;
+            bit = (j == 0) ? (symbol >= kNumLowLenSymbols) : (symbol >= kNumLowLenSymbols + kNumMidLenSymbols);
+        } else if (j < nchoice + nbits) {
+            tree_decision(j - nchoice, tree, nbits, sym, ptr, bit);
+        }
+        return nchoice + nbits;
+    }
+    // literal (LiteralEncoder.Encoder2.encode / encodeMatched :17-40): decision j codes bit 7-j
+    __device__ __forceinline__ void literal_decision(int j, uint16_t* probs, bool matched, uint32_t match_byte, uint32_t symbol,
+                                                     uint16_t*& ptr, uint32_t& bit) const {
+        const int i = 7 - j;
+        uint32_t index = (0x100u | symbol) >> (i + 1);
+        bit = (symbol >> i) & 1;
+        if (matched && (((match_byte ^ symbol) & 0xFF) >> (i + 1)) == 0) index += (1 + ((match_byte >> i) & 1)) << 8;
+        ptr = probs + index;
+    }
+
     // Encoder2.GetPrice (:42-64): lanes 0..7 price one bit each; bit i uses the matched
     // context while every higher bit of symbol and match_byte agrees.  Uniform result.
     __device__ uint32_t lit_price(const uint16_t* probs, bool match_mode, uint32_t match_byte, uint32_t symbol) const {
@@ -525,12 +554,12 @@ struct Enc {
     // make nodes (len_end, need] usable: spill the nodes their slots still hold, then price = infinity
     __device__ void extend(int& len_end, int& wb, int need) {
         if (need <= len_end) return;
-        const int new_wb = need - (int)rmask;  // need - R + 1
+        const int new_wb = need - (int)rsize + 1;
         if (new_wb > wb) {
             __syncwarp();
             const uint4* src = reinterpret_cast<const uint4*>(ring);
             uint4* dst = reinterpret_cast<uint4*>(gopt);
-            for (int k = 2 * wb + lane; k < 2 * new_wb; k += 32) dst[k] = src[(uint32_t)k & (2 * rmask + 1)];
+            for (int k = 2 * wb + lane; k < 2 * new_wb; k += 32) dst[k] = src[2 * slot((uint32_t)k >> 1) + (k & 1)];
             wb = new_wb;
             __syncwarp();
         }
@@ -553,7 +582,7 @@ struct Enc {
         if (wb > 0) {
             const uint4* src = reinterpret_cast<const uint4*>(ring);
             uint4* dst = reinterpret_cast<uint4*>(gopt);
-            for (int k = 2 * wb + lane; k < 2 * (cur + 1); k += 32) dst[k] = src[(uint32_t)k & (2 * rmask + 1)];
+            for (int k = 2 * wb + lane; k < 2 * (cur + 1); k += 32) dst[k] = src[2 * slot((uint32_t)k >> 1) + (k & 1)];
             base = gopt;
             __syncwarp();
         }
@@ -592,6 +621,7 @@ struct Enc {
     }
 
     __device__ int get_optimum(uint32_t position, uint32_t* back_out);
+    __device__ void emit_match(uint32_t ps, int len, uint32_t pos, int slot);
     __device__ void flush_stream(uint32_t now);
     __device__ bool encode_one();
     __device__ void run();
@@ -733,13 +763,13 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
     uint32_t last_byte = current_byte;  // data[c] of the previous step
     for (;;) {  // :505-810
         cur++;
-        if (cur == len_end) return backward(cur, wb, back_out);
+        if (cur == len_end) break;
         int new_len = read_match_distances();
         num_distance_pairs = num_pairs;
         if (new_len >= fb) {
             longest_len = new_len;
             longest_found = true;
-            return backward(cur, wb, back_out);
+            break;
         }
         position++;
         c = m - 1;
@@ -814,43 +844,6 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
         if (kNumOpts - 1 - cur < num_avail_full) num_avail_full = kNumOpts - 1 - cur;
         num_avail = num_avail_full < fb ? num_avail_full : fb;
 
-        // match + literal + rep0 continuations of this position's pairs (:766-770): two bytes per lane and pair
-        if (num_avail_full >= 2 && num_distance_pairs > 0) {
-            for (int j0 = 0; j0 < num_distance_pairs; j0 += 4) {
-                uint32_t xa[4], xb[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int j = j0 + u;
-                    xa[u] = 0;
-                    xb[u] = 1;
-                    if (j < num_distance_pairs) {
-                        int lj = md_len(j);
-                        if (lj > num_avail) lj = num_avail;  // the truncation of :737-743
-                        const uint32_t s = c + lj + 1 + lane;
-                        if (s < n) {
-                            xa[u] = data[s];
-                            xb[u] = data[s - md_dist(j) - 1];
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int j = j0 + u;
-                    const unsigned e = __ballot_sync(kFull, xa[u] == xb[u]);
-                    if (j < num_distance_pairs) {
-                        int lj = md_len(j);
-                        if (lj > num_avail) lj = num_avail;
-                        int l2 = 0;
-                        if (lj < num_avail_full) {
-                            const int t = num_avail_full - 1 - lj < fb ? num_avail_full - 1 - lj : fb;
-                            l2 = eq_run(e, 0, c + lj + 1, md_dist(j), t);
-                        }
-                        if (lane == 0) md2[j] = (uint16_t)l2;
-                    }
-                }
-            }
-        }
-
 #pragma unroll
         for (int i = 0; i < 4; i++) eq[i] = __ballot_sync(kFull, inr && a_byte == b_byte[i]);
         current_byte = __shfl_sync(kFull, a_byte, 0);
@@ -924,11 +917,14 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
         const bool do_matches = new_len >= start_len;
         if (do_matches) {
             if (cur + new_len > need) need = cur + new_len;
-            __syncwarp();  // md2 written above
+            // "match + literal + rep0" (:766-770): the continuation length was precomputed by the
+            // match finder up to fb; it is only asked for when the pair is not the truncated one
             for (int j = 0; j < num_distance_pairs; j++) {
                 const int lj = md_len(j);
-                if (lj < start_len) continue;
-                const int l2 = md2[j];
+                if (lj < start_len || lj >= num_avail_full) continue;
+                const int t = num_avail_full - 1 - lj;
+                int l2 = md2[j];
+                if (l2 > t) l2 = t;
                 if (l2 >= 2 && cur + lj + 1 + l2 > need) need = cur + lj + 1 + l2;
             }
         }
@@ -947,7 +943,7 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
         }
 
         // ---- reps (:669-735)
-#pragma unroll
+#pragma unroll 1
         for (int rep_index = 0; rep_index < kNumRepDistances; rep_index++) {
             const int lt = len_test[rep_index];
             if (lt < 2) continue;
@@ -989,8 +985,10 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
             normal_match_price = match_price + price0(*p_is_rep(st));
             for (int j = 0; j < num_distance_pairs; j++) {
                 const int lj = md_len(j);
-                if (lj < start_len) continue;
-                const int l2 = md2[j];
+                if (lj < start_len || lj >= num_avail_full) continue;
+                const int t = num_avail_full - 1 - lj;
+                int l2 = md2[j];
+                if (l2 > t) l2 = t;
                 if (l2 < 2) continue;
                 const uint32_t cur_back = md_dist(j);
                 const uint32_t cur_and_len_price = normal_match_price + pos_len_price(cur_back, lj, pos_state);
@@ -1018,25 +1016,55 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
             __syncwarp();
         }
     }
+    return backward(cur, wb, back_out);
+}
+
+// one match-type symbol: isMatch=1, isRep=0, length, posSlot, footer (encodeAMatch :976-1005 and
+// WriteEndMarker :818-835 which is the same symbol with len 2 and an all-ones 32-bit "distance")
+__device__ void Enc::emit_match(uint32_t ps, int len, uint32_t pos, int slot) {
+    uint16_t* ptr = model;
+    uint32_t bit = 0;
+    // batch 1: isMatch, isRep, length coder, posSlot tree
+    int cnt = 2;
+    if (lane == 0) { ptr = p_is_match(state, ps); bit = 1; }
+    if (lane == 1) { ptr = p_is_rep(state); bit = 0; }
+    const int nlen = len_decisions(lane - 2, 0, (uint32_t)(len - kMatchMinLen), ps, ptr, bit);
+    cnt += nlen;
+    if (lane >= cnt && lane < cnt + kNumPosSlotBits)
+        tree_decision(lane - cnt, model + L.pos_slot + (len_to_pos_state(len) << kNumPosSlotBits), kNumPosSlotBits, (uint32_t)slot, ptr, bit);
+    cnt += kNumPosSlotBits;
+    rc.batch(cnt, ptr, bit, false);
+    // batch 2: footer
+    if (slot >= kStartPosModelIndex) {
+        const int footer_bits = (slot >> 1) - 1;
+        const uint32_t base = (2u | (slot & 1)) << footer_bits;
+        const uint32_t pos_reduced = pos - base;
+        bool direct = false;
+        if (slot < kEndPosModelIndex) {
+            if (lane < footer_bits) reverse_decision(lane, model + L.pos_dec + base - slot - 1, pos_reduced, ptr, bit);
+            cnt = footer_bits;
+        } else {
+            const int ndirect = footer_bits - kNumAlignBits;  // encodeDirectBits(posReduced >> 4, ndirect): MSB first
+            if (lane < ndirect) {
+                direct = true;
+                bit = ((pos_reduced >> kNumAlignBits) >> (ndirect - 1 - lane)) & 1;
+            } else if (lane < footer_bits) {
+                reverse_decision(lane - ndirect, model + L.pos_align, pos_reduced & kAlignMask, ptr, bit);
+            }
+            cnt = footer_bits;
+        }
+        rc.batch(cnt, ptr, bit, direct);
+    }
 }
 
 __device__ void Enc::flush_stream(uint32_t now) {  // Encoder.java:837-841 + WriteEndMarker :818-835
     const uint32_t ps = now & pos_mask;
-    if (lane == 0) {
-        if (eos) {
-            rc.encode(p_is_match(state, ps), 1);
-            rc.encode(p_is_rep(state), 0);
-            len_encode_bits(0, 0, ps);
-            const uint32_t slot = (1u << kNumPosSlotBits) - 1;
-            rc.tree(model + L.pos_slot + (len_to_pos_state(kMatchMinLen) << kNumPosSlotBits), kNumPosSlotBits, slot);
-            const int footer_bits = 30;
-            const uint32_t pos_reduced = (1u << footer_bits) - 1;
-            rc.direct(pos_reduced >> kNumAlignBits, footer_bits - kNumAlignBits);
-            rc.reverse(model + L.pos_align, kNumAlignBits, pos_reduced & kAlignMask);
-        }
-        rc.flush();
+    if (eos) {
+        // len = 2, posSlot = 63, posReduced = 2^30 - 1 (26 direct one-bits, align 15): pos - base with base = 3 << 30
+        emit_match(ps, kMatchMinLen, 0xFFFFFFFFu, (1 << kNumPosSlotBits) - 1);
+        state = st_match(state);
     }
-    if (eos) state = st_match(state);
+    rc.flush();
     __syncwarp();
 }
 
@@ -1046,41 +1074,37 @@ __device__ bool Enc::encode_one() {
     const int len = get_optimum(now_pos, &back);
     const uint32_t ps = now_pos & pos_mask;
     __syncwarp();
-    if (len == 1 && back == kLit) {
-        const uint32_t cur_byte = byte_at(0 - additional_offset);  // encodeSingleByteLiteral :1007-1024
-        if (lane == 0) {
-            rc.encode(p_is_match(state, ps), 0);
-            uint16_t* sub = lit_coder(now_pos, prev_byte);
-            if (st_is_char(state)) {
-                lit_encode(sub, cur_byte);
-            } else {
-                const uint32_t mb = byte_at(0 - (int)rep_dist[0] - 1 - additional_offset);
-                lit_encode_matched(sub, mb, cur_byte);
-            }
-        }
+    uint16_t* ptr = model;
+    uint32_t bit = 0;
+    if (len == 1 && back == kLit) {  // encodeSingleByteLiteral :1007-1024
+        const uint32_t cur_byte = byte_at(0 - additional_offset);
+        const bool matched = !st_is_char(state);
+        uint32_t mb = 0;
+        if (matched) mb = byte_at(0 - (int)rep_dist[0] - 1 - additional_offset);
+        if (lane == 0) { ptr = p_is_match(state, ps); bit = 0; }
+        else if (lane <= 8) literal_decision(lane - 1, lit_coder(now_pos, prev_byte), matched, mb, cur_byte, ptr, bit);
+        rc.batch(9, ptr, bit, false);
         prev_byte = cur_byte;
         state = st_lit(state);
-        __syncwarp();
     } else {
         if (back < kNumRepDistances) {  // encodeARepetition :938-974
-            if (lane == 0) {
-                rc.encode(p_is_match(state, ps), 1);
-                rc.encode(p_is_rep(state), 1);
-                if (back == 0) {
-                    rc.encode(p_is_rep_g0(state), 0);
-                    rc.encode(p_is_rep0_long(state, ps), len == 1 ? 0 : 1);
-                } else {
-                    rc.encode(p_is_rep_g0(state), 1);
-                    if (back == 1) {
-                        rc.encode(p_is_rep_g1(state), 0);
-                    } else {
-                        rc.encode(p_is_rep_g1(state), 1);
-                        rc.encode(p_is_rep_g2(state), back - 2);
-                    }
+            int cnt;
+            if (lane == 0) { ptr = p_is_match(state, ps); bit = 1; }
+            if (lane == 1) { ptr = p_is_rep(state); bit = 1; }
+            if (lane == 2) { ptr = p_is_rep_g0(state); bit = back != 0; }
+            if (back == 0) {
+                if (lane == 3) { ptr = p_is_rep0_long(state, ps); bit = len != 1; }
+                cnt = 4;
+            } else {
+                if (lane == 3) { ptr = p_is_rep_g1(state); bit = back != 1; }
+                cnt = 4;
+                if (back != 1) {
+                    if (lane == 4) { ptr = p_is_rep_g2(state); bit = back - 2; }
+                    cnt = 5;
                 }
-                if (len != 1) len_encode_bits(1, len - kMatchMinLen, ps);
             }
-            __syncwarp();
+            if (len != 1) cnt += len_decisions(lane - cnt, 1, (uint32_t)(len - kMatchMinLen), ps, ptr, bit);
+            rc.batch(cnt, ptr, bit, false);
             if (len == 1) {
                 state = st_shortrep(state);
             } else {
@@ -1097,24 +1121,7 @@ __device__ bool Enc::encode_one() {
         } else {  // encodeAMatch :976-1005
             const uint32_t pos = back - kNumRepDistances;
             const int slot = pos_slot(pos);
-            if (lane == 0) {
-                rc.encode(p_is_match(state, ps), 1);
-                rc.encode(p_is_rep(state), 0);
-                len_encode_bits(0, len - kMatchMinLen, ps);
-                rc.tree(model + L.pos_slot + (len_to_pos_state(len) << kNumPosSlotBits), kNumPosSlotBits, slot);
-                if (slot >= kStartPosModelIndex) {
-                    const int footer_bits = (slot >> 1) - 1;
-                    const uint32_t base = (2u | (slot & 1)) << footer_bits;
-                    const uint32_t pos_reduced = pos - base;
-                    if (slot < kEndPosModelIndex) {
-                        rc.reverse(model + L.pos_dec + base - slot - 1, footer_bits, pos_reduced);
-                    } else {
-                        rc.direct(pos_reduced >> kNumAlignBits, footer_bits - kNumAlignBits);
-                        rc.reverse(model + L.pos_align, kNumAlignBits, pos_reduced & kAlignMask);
-                    }
-                }
-            }
-            __syncwarp();
+            emit_match(ps, len, pos, slot);
             state = st_match(state);
             len_count(0, ps);
             if (slot >= kEndPosModelIndex) align_price_count++;
@@ -1149,8 +1156,10 @@ __device__ void Enc::run() {
     opt_end = opt_cur = 0;
     additional_offset = 0;
     m = 0;
-    pre_pos = 0;
-    pre_off = kMfEmpty;
+    pf_pos = 0xFFFFFFFFu;
+    pf_off_pos = 0xFFFFFFFFu;
+    pf_off = kMfEmpty;
+    pf_cnt = pf_pair = pf_l2 = pf_from = 0;
     now_pos = 0;
     num_pairs = 0;
     match_price_count = 0;
@@ -1167,11 +1176,13 @@ __device__ void Enc::run() {
     }
     read_match_distances();  // first byte is always a plain literal (:860-878)
     const uint32_t cur_byte = byte_at(0 - additional_offset);
-    if (lane == 0) {
-        rc.encode(p_is_match(state, 0), 0);
-        lit_encode(lit_coder(0, prev_byte), cur_byte);
+    {
+        uint16_t* ptr = model;
+        uint32_t bit = 0;
+        if (lane == 0) { ptr = p_is_match(state, 0); bit = 0; }
+        else if (lane <= 8) literal_decision(lane - 1, lit_coder(0, prev_byte), false, 0, cur_byte, ptr, bit);
+        rc.batch(9, ptr, bit, false);
     }
-    __syncwarp();
     state = st_lit(state);
     prev_byte = cur_byte;
     additional_offset--;
@@ -1244,13 +1255,15 @@ __global__ void __launch_bounds__(kEncMaxWarps * 32, 1) lzb_parse_kernel(ParseAr
         e.md = reinterpret_cast<uint32_t*>(slice + S.md);
         e.md2 = reinterpret_cast<uint16_t*>(slice + S.md2);
         e.ring = reinterpret_cast<OptNode*>(slice + S.ring);
-        e.rmask = S.ring_nodes - 1;
+        e.rsize = S.ring_nodes;
+        e.rinv = ((1u << 24) + S.ring_nodes - 1) / S.ring_nodes;
         e.gopt = reinterpret_cast<OptNode*>(a.opt_scratch) + slot * (size_t)kNumOpts;
         e.L = L;
         e.data = a.mf.in + a.mf.in_off[b];
         e.n = n;
         e.idx = a.mf.idx + (size_t)b * a.mf.np;
         e.pairs = a.mf.pairs + (size_t)b * a.mf.pair_cap;
+        e.pairs2 = a.mf.pairs2 + (size_t)b * a.mf.pair_cap;
         e.lane = lane;
         e.lc = a.lc;
         e.lp = a.lp;
@@ -1261,7 +1274,7 @@ __global__ void __launch_bounds__(kEncMaxWarps * 32, 1) lzb_parse_kernel(ParseAr
         e.pos_mask = (1u << a.pb) - 1;
         e.lp_mask = (1u << a.lp) - 1;
         e.eos = a.eos;
-        e.rc.init(out, cap);
+        e.rc.init(out, cap, lane);
         e.run();
         if (lane == 0) a.out_len[b] = e.rc.pos > cap ? ~0ull : e.rc.pos + header;
         __syncwarp();
