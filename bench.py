@@ -396,7 +396,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=4096, help="decode streams per GPU (configs[1]: 4096)")
-    ap.add_argument("--enc-blocks", type=int, default=512, help="1 MiB blocks per GPU for the encode extra")
+    ap.add_argument("--enc-blocks", type=int, default=1024, help="1 MiB blocks per GPU for the encode extra")
     ap.add_argument("--enc-steps", type=int, default=2)
     ap.add_argument("--enc-cpu-blocks", type=int, default=128)
     ap.add_argument("--no-encode", action="store_true")

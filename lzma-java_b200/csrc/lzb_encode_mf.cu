@@ -162,6 +162,10 @@ __global__ void __launch_bounds__(256) lzb_mf_tree_kernel(MfWave w) {
                 break;
             }
             const uint8_t* pby1 = buf + cm;
+            // both children of the candidate in one 8-byte load, issued together with the first byte
+            // compare: one dependent memory round trip per tree level instead of two.  (The slots
+            // written below belong to other nodes, never to `cm`, so reading early is safe.)
+            const uint2 kids = *reinterpret_cast<const uint2*>(son + 2 * cm);
             uint32_t len = len0 < len1 ? len0 : len1;
             if (pby1[len] == cur[len]) {
                 while (++len != len_limit)
@@ -170,8 +174,8 @@ __global__ void __launch_bounds__(256) lzb_mf_tree_kernel(MfWave w) {
                     max_len = len;
                     pairs[cnt++] = (len << kPairDistBits) | (pos1 - cm - 1);
                     if (len == len_limit) {
-                        son[ptr1] = son[2 * cm];
-                        son[ptr0] = son[2 * cm + 1];
+                        son[ptr1] = kids.x;
+                        son[ptr0] = kids.y;
                         break;
                     }
                 }
@@ -179,12 +183,12 @@ __global__ void __launch_bounds__(256) lzb_mf_tree_kernel(MfWave w) {
             if (pby1[len] < cur[len]) {
                 son[ptr1] = cm;
                 ptr1 = 2 * cm + 1;
-                cm = son[ptr1];
+                cm = kids.y;
                 len1 = len;
             } else {
                 son[ptr0] = cm;
                 ptr0 = 2 * cm;
-                cm = son[ptr0];
+                cm = kids.x;
                 len0 = len;
             }
         }

@@ -46,6 +46,7 @@ struct CtaTables {
 };
 
 __device__ void init_cta_tables(CtaTables* t) {
+    #pragma unroll 1
     for (int j = threadIdx.x; j < 512; j += blockDim.x) {
         uint32_t v = 0;  // entry 0 is never written by the reference and stays 0
         if (j > 0) {
@@ -55,6 +56,7 @@ __device__ void init_cta_tables(CtaTables* t) {
         }
         t->prob_prices[j] = (uint16_t)v;
     }
+    #pragma unroll 1
     for (int c = threadIdx.x; c < 2048; c += blockDim.x) {
         uint32_t s;
         if (c < 2) {
@@ -115,6 +117,7 @@ struct RangeEnc {
         const uint32_t low_hi = (uint32_t)(low >> 32);
         if (low_hi != 0 || low < 0xFF000000ull) {
             uint32_t temp = cache;
+            #pragma unroll 1
             do {
                 if (lane == 0 && pos < cap) out[pos] = (uint8_t)(temp + low_hi);
                 pos++;
@@ -202,6 +205,7 @@ __device__ __noinline__ int warp_match_len(const uint8_t* data, uint32_t n, int 
     const uint8_t* a = data + s;
     const uint8_t* b = a - distance - 1;
     int len = 0;
+    #pragma unroll 1
     while (len < limit) {
         const int i = len + lane;
         const bool ok = i < limit;
@@ -266,6 +270,7 @@ struct Enc {
     __device__ __forceinline__ uint32_t price1(uint32_t prob) const { return T->prob_prices[(kBitModelTotal - prob) >> 2]; }
     __device__ __forceinline__ uint32_t tree_price(const uint16_t* probs, int nbits, uint32_t symbol) const {  // BitTreeEncoder.java:38-48
         uint32_t price = 0, mm = 1;
+        #pragma unroll 1
         for (int bi = nbits; bi != 0;) {
             bi--;
             const uint32_t bit = (symbol >> bi) & 1;
@@ -276,6 +281,7 @@ struct Enc {
     }
     __device__ __forceinline__ uint32_t reverse_price(const uint16_t* probs, int nbits, uint32_t symbol) const {  // :50-60
         uint32_t price = 0, mm = 1;
+        #pragma unroll 1
         for (int i = nbits; i != 0; i--) {
             const uint32_t bit = symbol & 1;
             symbol >>= 1;
@@ -364,6 +370,7 @@ struct Enc {
             md[lane] = pf_pair;
             md2[lane] = (uint16_t)pf_l2;
         }
+        #pragma unroll 1
         for (int i = 32 + lane; i < cnt; i += 32) {
             md[i] = pairs[pf_from + 1 + i];
             md2[i] = pairs2[pf_from + 1 + i];
@@ -398,6 +405,7 @@ struct Enc {
         uint16_t* prices = len_prices + ((which << pb) + ps) * table_size;
         const uint32_t a0 = price0(lp_[0]), a1 = price1(lp_[0]);
         const uint32_t b0 = a1 + price0(lp_[1]), b1 = a1 + price1(lp_[1]);
+        #pragma unroll 1
         for (int i = lane; i < table_size; i += 32) {
             uint32_t v;
             if (i < kNumLowLenSymbols) v = a0 + tree_price(lp_ + len_low(pb, ps), kNumLowLenBits, i);
@@ -520,6 +528,7 @@ struct Enc {
     __device__ void fill_distances_prices() {
         __syncwarp();
         // slot prices first (they do not depend on tempPrices)
+        #pragma unroll 1
         for (int k = lane; k < kNumLenToPosStates * dist_table_size; k += 32) {
             const int lps = k / dist_table_size, slot = k - lps * dist_table_size;
             uint32_t v = tree_price(model + L.pos_slot + (lps << kNumPosSlotBits), kNumPosSlotBits, slot);
@@ -527,6 +536,7 @@ struct Enc {
             slot_prices[(lps << kNumPosSlotBits) + slot] = (uint16_t)v;
         }
         __syncwarp();
+        #pragma unroll 1
         for (int k = lane; k < kNumLenToPosStates * kNumFullDistances; k += 32) {
             const int lps = k >> 7, i = k & (kNumFullDistances - 1);
             uint32_t v;
@@ -559,10 +569,12 @@ struct Enc {
             __syncwarp();
             const uint4* src = reinterpret_cast<const uint4*>(ring);
             uint4* dst = reinterpret_cast<uint4*>(gopt);
+            #pragma unroll 1
             for (int k = 2 * wb + lane; k < 2 * new_wb; k += 32) dst[k] = src[2 * slot((uint32_t)k >> 1) + (k & 1)];
             wb = new_wb;
             __syncwarp();
         }
+        #pragma unroll 1
         for (int t = len_end + 1 + lane; t <= need; t += 32) node(t)->price = kInfinityPrice;
         len_end = need;
     }
@@ -582,6 +594,7 @@ struct Enc {
         if (wb > 0) {
             const uint4* src = reinterpret_cast<const uint4*>(ring);
             uint4* dst = reinterpret_cast<uint4*>(gopt);
+            #pragma unroll 1
             for (int k = 2 * wb + lane; k < 2 * (cur + 1); k += 32) dst[k] = src[2 * slot((uint32_t)k >> 1) + (k & 1)];
             base = gopt;
             __syncwarp();
@@ -593,6 +606,7 @@ struct Enc {
             OptNode* opt = base;
             uint32_t pos_mem = ln_pos_prev(opt[cur].link);
             uint32_t back_mem = opt[cur].back_prev;
+            #pragma unroll 1
             do {
                 const uint32_t lk = opt[cur].link;
                 if (ln_prev1(lk)) {
@@ -734,13 +748,16 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
         o1->back_prev = back1;
         o1->link = mk_link(0, 0, false, false);
     }
+    #pragma unroll 1
     for (int len = 2 + lane; len <= len_end; len += 32) node(len)->price = kInfinityPrice;  // :451-455
     __syncwarp();
 
+    #pragma unroll 1
     for (int i = 0; i < kNumRepDistances; i++) {  // :457-474, one length per lane
         const int rep_len = (int)rep_lens[i];
         if (rep_len < 2) continue;
         const uint32_t price = rep_match_price + pure_rep_price(i, st, pos_state);
+        #pragma unroll 1
         for (int len = 2 + lane; len <= rep_len; len += 32)
             relax(len, price + len_price(1, len - 2, pos_state), 0, (uint32_t)i, false, false, 0, 0);
         __syncwarp();
@@ -749,8 +766,10 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
     uint32_t normal_match_price = match_price + price0(*p_is_rep(st));
     {
         const int start = rep_lens[0] >= 2 ? (int)rep_lens[0] + 1 : 2;  // :478-501
+        #pragma unroll 1
         for (int len = start + lane; len <= len_main; len += 32) {
             int offs = 0;
+            #pragma unroll 1
             while (len > md_len(offs)) offs++;
             const uint32_t distance = md_dist(offs);
             relax(len, normal_match_price + pos_len_price(distance, len, pos_state), 0, distance + kNumRepDistances, false, false,
@@ -761,6 +780,7 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
 
     int cur = 0;
     uint32_t last_byte = current_byte;  // data[c] of the previous step
+    #pragma unroll 1
     for (;;) {  // :505-810
         cur++;
         if (cur == len_end) break;
@@ -908,6 +928,7 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
         const int start_len = len_test[0] >= 2 ? len_test[0] + 1 : 2;  // :667, :691-693
         if (new_len > num_avail) {  // :737-743
             new_len = num_avail;
+            #pragma unroll 1
             for (num_distance_pairs = 0; new_len > md_len(num_distance_pairs); num_distance_pairs++) {}
             __syncwarp();
             if (lane == 0) md[num_distance_pairs] = ((uint32_t)new_len << kPairDistBits) | md_dist(num_distance_pairs);
@@ -919,6 +940,7 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
             if (cur + new_len > need) need = cur + new_len;
             // "match + literal + rep0" (:766-770): the continuation length was precomputed by the
             // match finder up to fb; it is only asked for when the pair is not the truncated one
+            #pragma unroll 1
             for (int j = 0; j < num_distance_pairs; j++) {
                 const int lj = md_len(j);
                 if (lj < start_len || lj >= num_avail_full) continue;
@@ -948,6 +970,7 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
             const int lt = len_test[rep_index];
             if (lt < 2) continue;
             const uint32_t rp = rep_match_price + pure_rep_price(rep_index, st, pos_state);
+            #pragma unroll 1
             for (int len = 2 + lane; len <= lt; len += 32)
                 relax(cur + len, rp + len_price(1, len - 2, pos_state), (uint32_t)cur, (uint32_t)rep_index, false, false, 0, 0);
             __syncwarp();
@@ -983,6 +1006,7 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
         // (they come up at the pair boundary l), so all continuations go first, in pair order.
         if (do_matches) {
             normal_match_price = match_price + price0(*p_is_rep(st));
+            #pragma unroll 1
             for (int j = 0; j < num_distance_pairs; j++) {
                 const int lj = md_len(j);
                 if (lj < start_len || lj >= num_avail_full) continue;
@@ -1006,8 +1030,10 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
                           true, (uint32_t)cur, cur_back + kNumRepDistances);
                 __syncwarp();
             }
+            #pragma unroll 1
             for (int len = start_len + lane; len <= new_len; len += 32) {
                 int offs = 0;
+                #pragma unroll 1
                 while (len > md_len(offs)) offs++;
                 const uint32_t cur_back = md_dist(offs);
                 relax(cur + len, normal_match_price + pos_len_price(cur_back, len, pos_state), (uint32_t)cur, cur_back + kNumRepDistances,
@@ -1150,6 +1176,7 @@ __device__ bool Enc::encode_one() {
 __device__ void Enc::run() {
     state = 0;
     prev_byte = 0;
+    #pragma unroll 1
     for (int i = 0; i < 4; i++) rep_dist[i] = 0;
     longest_found = false;
     longest_len = 0;
@@ -1167,7 +1194,9 @@ __device__ void Enc::run() {
     qbase = ring;
     fill_distances_prices();
     fill_align_prices();
+    #pragma unroll 1
     for (int which = 0; which < 2; which++)
+        #pragma unroll 1
         for (uint32_t ps = 0; ps < (1u << pb); ps++) len_update_table(which, ps);
 
     if (avail() == 0) {
@@ -1191,6 +1220,7 @@ __device__ void Enc::run() {
         flush_stream(now_pos);
         return;
     }
+    #pragma unroll 1
     while (encode_one()) {}
 }
 
@@ -1207,6 +1237,7 @@ __global__ void __launch_bounds__(kEncMaxWarps * 32, 1) lzb_parse_kernel(ParseAr
     uint16_t* model = reinterpret_cast<uint16_t*>(slice);
     uint16_t* lit = S.lit_in_smem ? model + L.literal : a.lit_scratch + slot * (size_t)L.n_literal;
 
+    #pragma unroll 1
     for (;;) {
         uint32_t b = 0;
         if (lane == 0) b = atomicAdd(a.ticket, 1u);
@@ -1235,11 +1266,14 @@ __global__ void __launch_bounds__(kEncMaxWarps * 32, 1) lzb_parse_kernel(ParseAr
         }
         // Encoder.Init (:247-273): every probability = 1024; price tables start from Java's zero-init (App. A #14)
         __syncwarp();
+        #pragma unroll 1
         for (int i = lane; i < L.n_fixed; i += 32) model[i] = kProbInit;
+        #pragma unroll 1
         for (int i = lane; i < L.n_literal; i += 32) lit[i] = kProbInit;
         {
             uint32_t* z = reinterpret_cast<uint32_t*>(slice + S.dist_prices);
             const uint32_t words = (S.ring - S.dist_prices) / 4;
+            #pragma unroll 1
             for (uint32_t i = lane; i < words; i += 32) z[i] = 0;
         }
         __syncwarp();
