@@ -192,7 +192,9 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        dist.init_process_group("nccl", device_id=dev)
+        # gloo: the data path has no collective (independent streams); the process group only
+        # carries the contract's barrier and the max-over-ranks of the timings
+        dist.init_process_group("gloo")
 
     def barrier():
         if dist is not None:
@@ -201,14 +203,14 @@ def run_b200(args, rank, world, local_rank):
     def max_over_ranks(x):
         if dist is None:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        t = torch.tensor([x], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
     def sum_over_ranks(x):
         if dist is None:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        t = torch.tensor([x], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
