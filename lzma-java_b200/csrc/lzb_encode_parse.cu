@@ -112,12 +112,13 @@ struct RangeEnc {
         cap = c;
         lane = l;
     }
-    __device__ __noinline__ static void shift_low_impl(uint64_t& low, uint32_t& cache_size, uint32_t& cache, uint8_t* out,
-                                                       uint64_t& pos, uint64_t cap, int lane) {  // :73-87
+    // RangeEncoder.shiftLow (:73-87).  Inline on purpose: an out-of-line call would take the address
+    // of the coder state and push the whole parser state into local memory.
+    __device__ __forceinline__ void shift_low() {
         const uint32_t low_hi = (uint32_t)(low >> 32);
         if (low_hi != 0 || low < 0xFF000000ull) {
             uint32_t temp = cache;
-            #pragma unroll 1
+#pragma unroll 1
             do {
                 if (lane == 0 && pos < cap) out[pos] = (uint8_t)(temp + low_hi);
                 pos++;
@@ -128,7 +129,6 @@ struct RangeEnc {
         cache_size++;
         low = (low & 0xFFFFFF) << 8;
     }
-    __device__ __forceinline__ void shift_low() { shift_low_impl(low, cache_size, cache, out, pos, cap, lane); }
     __device__ __forceinline__ void flush() {  // :31-36
 #pragma unroll 1
         for (int i = 0; i < 5; i++) shift_low();
@@ -200,7 +200,7 @@ __host__ __device__ inline SliceLayout make_slice(int lc, int lp, int pb, int fb
 
 // InWindow.GetMatchLen (InWindow.java:120-134) from absolute position `s`, 32 bytes per round;
 // every lane returns the same value.  Out of line: it is the rare continuation of a bitmap run.
-__device__ __noinline__ int warp_match_len(const uint8_t* data, uint32_t n, int lane, uint32_t s, uint32_t distance, int limit) {
+__device__ __forceinline__ int warp_match_len(const uint8_t* data, uint32_t n, int lane, uint32_t s, uint32_t distance, int limit) {
     if (limit > 0 && s + (uint32_t)limit > n) limit = (int)(n - s);
     const uint8_t* a = data + s;
     const uint8_t* b = a - distance - 1;
@@ -219,6 +219,13 @@ __device__ __noinline__ int warp_match_len(const uint8_t* data, uint32_t n, int 
         len += 32;
     }
     return limit > 0 ? limit : 0;
+}
+
+// element i of a 4-array without dynamic indexing (which would push the array -- and the struct
+// around it -- into local memory)
+template <typename T>
+__device__ __forceinline__ T sel4(const T (&a)[4], int i) {
+    return i == 0 ? a[0] : (i == 1 ? a[1] : (i == 2 ? a[2] : a[3]));
 }
 
 // ---- everything one stream needs (identical in every lane unless noted) -----
@@ -362,7 +369,7 @@ struct Enc {
         if (p + 1 < n) pf_off = idx[p + 2];
     }
 
-    __device__ int read_match_distances() {  // Encoder.java:275-287
+    __device__ __forceinline__ int read_match_distances() {  // Encoder.java:275-287
         __syncwarp();  // everyone is done with the previous list
         if (pf_pos != m) prefetch_list(m);
         const int cnt = (int)pf_cnt;
@@ -399,7 +406,7 @@ struct Enc {
         return len_prices[((which << pb) + ps) * table_size + symbol];
     }
     // LenEncoder.SetPrices :50-71 + UpdateTable :20-23, one lane per symbol
-    __device__ void len_update_table(int which, uint32_t ps) {
+    __device__ __forceinline__ void len_update_table(int which, uint32_t ps) {
         __syncwarp();
         const uint16_t* lp_ = model + (which ? L.rep_len : L.len);
         uint16_t* prices = len_prices + ((which << pb) + ps) * table_size;
@@ -417,7 +424,7 @@ struct Enc {
         __syncwarp();
     }
     // all lanes, after the bits were emitted: LenPriceTableEncoder.encode :32-37
-    __device__ void len_count(int which, uint32_t ps) {
+    __device__ __forceinline__ void len_count(int which, uint32_t ps) {
         const int c = len_counters[which * 16 + ps] - 1;
         __syncwarp();
         if (c == 0) {
@@ -475,7 +482,7 @@ struct Enc {
 
     // Encoder2.GetPrice (:42-64): lanes 0..7 price one bit each; bit i uses the matched
     // context while every higher bit of symbol and match_byte agrees.  Uniform result.
-    __device__ uint32_t lit_price(const uint16_t* probs, bool match_mode, uint32_t match_byte, uint32_t symbol) const {
+    __device__ __forceinline__ uint32_t lit_price(const uint16_t* probs, bool match_mode, uint32_t match_byte, uint32_t symbol) const {
         uint32_t price = 0;
         if (lane < 8) {
             const int i = 7 - lane;
@@ -495,7 +502,7 @@ struct Enc {
     __device__ __forceinline__ uint32_t rep_len1_price(int st, uint32_t ps) const {
         return price0(*p_is_rep_g0(st)) + price0(*p_is_rep0_long(st, ps));
     }
-    __device__ uint32_t pure_rep_price(int rep_index, int st, uint32_t ps) const {
+    __device__ __forceinline__ uint32_t pure_rep_price(int rep_index, int st, uint32_t ps) const {
         uint32_t price;
         if (rep_index == 0) {
             price = price0(*p_is_rep_g0(st));
@@ -525,7 +532,7 @@ struct Enc {
     }
 
     // ---- price table refresh (Encoder.java:1087-1125), one lane per entry ----
-    __device__ void fill_distances_prices() {
+    __device__ __forceinline__ void fill_distances_prices() {
         __syncwarp();
         // slot prices first (they do not depend on tempPrices)
         #pragma unroll 1
@@ -553,7 +560,7 @@ struct Enc {
         __syncwarp();
         match_price_count = 0;
     }
-    __device__ void fill_align_prices() {
+    __device__ __forceinline__ void fill_align_prices() {
         __syncwarp();
         if (lane < kAlignTableSize) align_prices[lane] = (uint16_t)reverse_price(model + L.pos_align, kNumAlignBits, lane);
         __syncwarp();
@@ -562,7 +569,7 @@ struct Enc {
 
     // ---- node ring management ----
     // make nodes (len_end, need] usable: spill the nodes their slots still hold, then price = infinity
-    __device__ void extend(int& len_end, int& wb, int need) {
+    __device__ __forceinline__ void extend(int& len_end, int& wb, int need) {
         if (need <= len_end) return;
         const int new_wb = need - (int)rsize + 1;
         if (new_wb > wb) {
@@ -588,7 +595,7 @@ struct Enc {
 
     // Backward (Encoder.java:335-362).  Runs on lane 0 over `base` (ring when the chunk never
     // wrapped, else the global spill area after the live part of the ring has been flushed).
-    __device__ int backward(int cur, int wb, uint32_t* back_out) {
+    __device__ __forceinline__ int backward(int cur, int wb, uint32_t* back_out) {
         __syncwarp();
         OptNode* base = ring;
         if (wb > 0) {
@@ -634,16 +641,16 @@ struct Enc {
         return opt_cur;
     }
 
-    __device__ int get_optimum(uint32_t position, uint32_t* back_out);
-    __device__ void emit_match(uint32_t ps, int len, uint32_t pos, int slot);
-    __device__ void flush_stream(uint32_t now);
-    __device__ bool encode_one();
-    __device__ void run();
+    __device__ __forceinline__ int get_optimum(uint32_t position, uint32_t* back_out);
+    __device__ __forceinline__ void emit_match(uint32_t ps, int len, uint32_t pos, int slot);
+    __device__ __forceinline__ void flush_stream(uint32_t now);
+    __device__ __forceinline__ bool encode_one();
+    __device__ __forceinline__ void run();
 };
 
 // getOptimum (Encoder.java:364-811).  Returns the length, *back_out = "pos" of PosAndLength
 // (kLit literal, 0..3 rep index, else distance + 4).  Uniform across the warp.
-__device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
+__device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
     if (opt_end != opt_cur) {  // :365-370
         const OptNode* q = qbase + opt_cur;
         const uint32_t lk = q->link;
@@ -689,11 +696,15 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
         eq[i] = __ballot_sync(kFull, in_range && a_byte == b_byte[i]);
         rep_lens[i] = (uint32_t)eq_run(eq[i], 0, c, reps[i], kMatchMaxLen);
     }
+    uint32_t rep_max_len = rep_lens[0];  // first index of the maximum (:396-398)
 #pragma unroll
     for (int i = 1; i < 4; i++)
-        if (rep_lens[i] > rep_lens[rep_max_index]) rep_max_index = i;
-    if ((int)rep_lens[rep_max_index] >= fb) {  // :400-404
-        const int len_res = (int)rep_lens[rep_max_index];
+        if (rep_lens[i] > rep_max_len) {
+            rep_max_index = i;
+            rep_max_len = rep_lens[i];
+        }
+    if ((int)rep_max_len >= fb) {  // :400-404
+        const int len_res = (int)rep_max_len;
         *back_out = (uint32_t)rep_max_index;
         move_pos(len_res - 1);
         return len_res;
@@ -707,7 +718,7 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
     uint32_t current_byte = __shfl_sync(kFull, a_byte, 0);
     uint32_t match_byte = __shfl_sync(kFull, b_byte[0], 0);
 
-    if (len_main < 2 && current_byte != match_byte && rep_lens[rep_max_index] < 2) {  // :415-417
+    if (len_main < 2 && current_byte != match_byte && rep_max_len < 2) {  // :415-417
         *back_out = kLit;
         return 1;
     }
@@ -729,7 +740,7 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
         }
     }
 
-    int len_end = len_main >= (int)rep_lens[rep_max_index] ? len_main : (int)rep_lens[rep_max_index];
+    int len_end = len_main >= (int)rep_max_len ? len_main : (int)rep_max_len;
     if (len_end < 2) {
         *back_out = back1;
         return 1;
@@ -754,7 +765,7 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
 
     #pragma unroll 1
     for (int i = 0; i < kNumRepDistances; i++) {  // :457-474, one length per lane
-        const int rep_len = (int)rep_lens[i];
+        const int rep_len = (int)sel4(rep_lens, i);
         if (rep_len < 2) continue;
         const uint32_t price = rep_match_price + pure_rep_price(i, st, pos_state);
         #pragma unroll 1
@@ -967,14 +978,14 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
         // ---- reps (:669-735)
 #pragma unroll 1
         for (int rep_index = 0; rep_index < kNumRepDistances; rep_index++) {
-            const int lt = len_test[rep_index];
+            const int lt = sel4(len_test, rep_index);
             if (lt < 2) continue;
             const uint32_t rp = rep_match_price + pure_rep_price(rep_index, st, pos_state);
             #pragma unroll 1
             for (int len = 2 + lane; len <= lt; len += 32)
                 relax(cur + len, rp + len_price(1, len - 2, pos_state), (uint32_t)cur, (uint32_t)rep_index, false, false, 0, 0);
             __syncwarp();
-            const int lt2 = len_test2[rep_index];
+            const int lt2 = sel4(len_test2, rep_index);
             if (lt2 >= 2) {  // rep + literal + rep0 (:696-734)
                 int state2 = st_longrep(st);
                 uint32_t ps_next = (position + lt) & pos_mask;
@@ -982,11 +993,11 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
                 if (lt < 32) {
                     sym = __shfl_sync(kFull, a_byte, lt);
                     prv = __shfl_sync(kFull, a_byte, lt - 1);
-                    mb = __shfl_sync(kFull, b_byte[rep_index], lt);
+                    mb = __shfl_sync(kFull, sel4(b_byte, rep_index), lt);
                 } else {
                     sym = data[c + lt];
                     prv = data[c + lt - 1];
-                    mb = data[c + lt - reps[rep_index] - 1];
+                    mb = data[c + lt - sel4(reps, rep_index) - 1];
                 }
                 const uint32_t cur_and_len_char_price = rp + len_price(1, lt - 2, pos_state) + price0(*p_is_match(state2, ps_next)) +
                                                         lit_price(lit_coder(position + lt, prv), true, mb, sym);
@@ -1047,7 +1058,7 @@ __device__ int Enc::get_optimum(uint32_t position, uint32_t* back_out) {
 
 // one match-type symbol: isMatch=1, isRep=0, length, posSlot, footer (encodeAMatch :976-1005 and
 // WriteEndMarker :818-835 which is the same symbol with len 2 and an all-ones 32-bit "distance")
-__device__ void Enc::emit_match(uint32_t ps, int len, uint32_t pos, int slot) {
+__device__ __forceinline__ void Enc::emit_match(uint32_t ps, int len, uint32_t pos, int slot) {
     uint16_t* ptr = model;
     uint32_t bit = 0;
     // batch 1: isMatch, isRep, length coder, posSlot tree
@@ -1083,7 +1094,7 @@ __device__ void Enc::emit_match(uint32_t ps, int len, uint32_t pos, int slot) {
     }
 }
 
-__device__ void Enc::flush_stream(uint32_t now) {  // Encoder.java:837-841 + WriteEndMarker :818-835
+__device__ __forceinline__ void Enc::flush_stream(uint32_t now) {  // Encoder.java:837-841 + WriteEndMarker :818-835
     const uint32_t ps = now & pos_mask;
     if (eos) {
         // len = 2, posSlot = 63, posReduced = 2^30 - 1 (26 direct one-bits, align 15): pos - base with base = 3 << 30
@@ -1095,7 +1106,7 @@ __device__ void Enc::flush_stream(uint32_t now) {  // Encoder.java:837-841 + Wri
 }
 
 // encodeOne (:890-936) with its emitters (:938-1024); false once the stream is flushed
-__device__ bool Enc::encode_one() {
+__device__ __forceinline__ bool Enc::encode_one() {
     uint32_t back;
     const int len = get_optimum(now_pos, &back);
     const uint32_t ps = now_pos & pos_mask;
@@ -1137,7 +1148,7 @@ __device__ bool Enc::encode_one() {
                 len_count(1, ps);
                 state = st_longrep(state);
             }
-            const uint32_t distance = rep_dist[back];
+            const uint32_t distance = sel4(rep_dist, (int)back);
             if (back != 0) {
                 if (back == 3) rep_dist[3] = rep_dist[2];
                 if (back >= 2) rep_dist[2] = rep_dist[1];
@@ -1173,11 +1184,10 @@ __device__ bool Enc::encode_one() {
 }
 
 // SetStreams + CodeOneBlock loop (Encoder.java:1046-1077, 843-888); probabilities already initialised
-__device__ void Enc::run() {
+__device__ __forceinline__ void Enc::run() {
     state = 0;
     prev_byte = 0;
-    #pragma unroll 1
-    for (int i = 0; i < 4; i++) rep_dist[i] = 0;
+    rep_dist[0] = rep_dist[1] = rep_dist[2] = rep_dist[3] = 0;
     longest_found = false;
     longest_len = 0;
     opt_end = opt_cur = 0;
