@@ -45,19 +45,31 @@ cudaError_t upload_mf_tables() {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
-// predecessor of `key` for this lane: nearest lower lane of the same key in
-// this step, else the table entry; the highest lane of the group updates the table.
-__device__ __forceinline__ uint32_t link_step(uint32_t* table, uint32_t key, unsigned vm, int lane, uint32_t base,
-                                              uint32_t pos1) {
-    const unsigned peers = __match_any_sync(vm, key);
-    const unsigned lower = peers & ((1u << lane) - 1u);
-    const uint32_t prev = lower ? base + 32u - (uint32_t)__clz(lower) : table[key];
-    __syncwarp(vm);  // every lane has read the table before the group leaders overwrite it
-    if ((peers >> lane) == 1u) table[key] = pos1;
-    return prev;
-}
+// One table replay for the lanes of this step.  Predecessor of `key` = nearest lower lane with
+// the same key in this step, else the table entry; the highest lane of each key group is the one
+// that will overwrite the table.  The table reads of all three hashes are issued first, the
+// writes follow after one __syncwarp, so a step costs one memory round trip, not three.
+struct LinkStep {
+    unsigned peers, lower;
+    uint32_t from_table;
+    __device__ __forceinline__ void read(const uint32_t* table, uint32_t key, unsigned vm, int lane) {
+        peers = __match_any_sync(vm, key);
+        lower = peers & ((1u << lane) - 1u);
+        from_table = 0;
+        if (!lower) from_table = table[key];
+    }
+    __device__ __forceinline__ uint32_t prev(uint32_t base) const {
+        return lower ? base + 32u - (uint32_t)__clz(lower) : from_table;
+    }
+    __device__ __forceinline__ void write(uint32_t* table, uint32_t key, int lane, uint32_t pos1) const {
+        if ((peers >> lane) == 1u) table[key] = pos1;
+    }
+};
 
 __global__ void __launch_bounds__(128) lzb_mf_link_kernel(MfWave w) {
+    __shared__ uint32_t s_crc[256];  // constant memory would serialise the 32 different indices of a warp
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = c_crc[i];
+    __syncthreads();
     const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (b >= w.n_blocks) return;
@@ -68,6 +80,7 @@ __global__ void __launch_bounds__(128) lzb_mf_link_kernel(MfWave w) {
     uint32_t* prev2 = w.prev2 + (size_t)b * w.np;
     uint32_t* prev3 = w.prev3 + (size_t)b * w.np;
     uint32_t* idx = w.idx + (size_t)b * w.np;
+    uint32_t* head3 = heads + kHash2Size;
     uint32_t* head4 = w.bt4 ? heads + kHash2Size + kHash3Size : heads;  // kFixHashSize, BinTree.java:57-69
     const uint32_t min_check = w.bt4 ? 4 : 3;                           // kMinMatchCheck
 
@@ -77,20 +90,33 @@ __global__ void __launch_bounds__(128) lzb_mf_link_kernel(MfWave w) {
         // positions with lenLimit < kMinMatchCheck are not inserted at all (BinTree.java:158-161)
         const bool valid = in_range && n - p >= min_check;
         const unsigned vm = __ballot_sync(kFull, valid);
+        uint32_t h2 = 0, h3 = 0, h4 = 0;
+        LinkStep s2, s3, s4;
         if (valid) {
-            uint32_t h4, c2 = 0, c3 = 0;
-            if (w.bt4) {
-                uint32_t t = c_crc[data[p]] ^ data[p + 1];
-                const uint32_t h2 = t & (kHash2Size - 1);
+            if (w.bt4) {  // BinTree.java:171-175
+                uint32_t t = s_crc[data[p]] ^ data[p + 1];
+                h2 = t & (kHash2Size - 1);
                 t ^= (uint32_t)data[p + 2] << 8;
-                const uint32_t h3 = t & (kHash3Size - 1);
-                h4 = (t ^ (c_crc[data[p + 3]] << 5)) & w.hash_mask;
-                c2 = link_step(heads, h2, vm, lane, base, pos1);
-                c3 = link_step(heads + kHash2Size, h3, vm, lane, base, pos1);
+                h3 = t & (kHash3Size - 1);
+                h4 = (t ^ (s_crc[data[p + 3]] << 5)) & w.hash_mask;
+                s2.read(heads, h2, vm, lane);
+                s3.read(head3, h3, vm, lane);
             } else {
                 h4 = data[p] ^ ((uint32_t)data[p + 1] << 8);
             }
-            const uint32_t prev4 = link_step(head4, h4, vm, lane, base, pos1);
+            s4.read(head4, h4, vm, lane);
+        }
+        __syncwarp();  // every lane has read the tables before the group leaders overwrite them
+        if (valid) {
+            uint32_t c2 = 0, c3 = 0;
+            if (w.bt4) {
+                c2 = s2.prev(base);
+                c3 = s3.prev(base);
+                s2.write(heads, h2, lane, pos1);
+                s3.write(head3, h3, lane, pos1);
+            }
+            const uint32_t prev4 = s4.prev(base);
+            s4.write(head4, h4, lane, pos1);
             if (prev4) next[prev4] = pos1;
             prev2[pos1] = c2 | (prev4 ? 0u : kHeadFlag);
             prev3[pos1] = c3;

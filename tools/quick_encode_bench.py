@@ -47,6 +47,7 @@ def main():
             best = ms if best is None else min(best, ms)
         print("iter %d: %.1f ms  %.3f GB/s in" % (it, ms, n * size / ms / 1e6), flush=True)
     csum = int(d_len.sum().item())
+    best = best if best is not None else ms
     print("OK n=%d size=%d cls=%d fb=%d best %.1f ms = %.3f GB/s, ratio %.3f" % (n, size, cls, fb, best, n * size / best / 1e6, csum / (n * size)))
 
 
