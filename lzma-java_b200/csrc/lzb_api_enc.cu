@@ -104,9 +104,10 @@ int lzb_enc_code_batch_device(lzb_enc* e, const uint8_t* d_in, const uint64_t* d
     if (n == 0) return LZB_OK;
     if (!d_in || !d_in_off || !d_in_len || !d_out || !d_out_off || !d_out_cap || !d_out_len)
         return fail(LZB_E_ARG, "null argument");
-    // BinTree.Create throws above 2^30 - 257 (BinTree.java:95-97); positions are 32-bit here as there.
-    if (max_in_len >= (1ull << 30) - 1) return fail(LZB_E_UNSUPPORTED, "block of %llu bytes: blocks must stay below 1 GiB",
-                                                    (unsigned long long)max_in_len);
+    // match pairs are packed as len << 23 | distance (BinTree.Create itself throws above 2^30 - 257, BinTree.java:95-97)
+    if (max_in_len > lzb::kEncMaxBlockBytes)
+        return fail(LZB_E_UNSUPPORTED, "block of %llu bytes: the encoder takes blocks of at most %llu bytes",
+                    (unsigned long long)max_in_len, (unsigned long long)lzb::kEncMaxBlockBytes);
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
     lzb::EncodeArgs a;

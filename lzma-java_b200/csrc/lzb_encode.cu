@@ -113,6 +113,7 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
     const size_t budget = std::max<size_t>((free_b + scratch.cap) / 2, size_t(256) << 20);
 
     uint32_t pair_mul = 8;  // pair slots per input byte; doubled when a wave overflows
+    if (const char* ev = getenv("LZB_PAIR_MUL")) pair_mul = (uint32_t)std::max(atoi(ev), 1);  // test knob for the retry path
     std::vector<uint64_t> h_off;  // unused; lengths stay on the device
 
     uint32_t done = 0;

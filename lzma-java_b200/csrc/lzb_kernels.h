@@ -60,6 +60,7 @@ struct EncScratch {
     void release();
 };
 
+constexpr uint64_t kEncMaxBlockBytes = 1ull << 23;  // match pairs pack len << 23 | distance
 constexpr int kEncMaxWarps = 9;            // parser streams resident per SM
 constexpr size_t kEncSliceBytes = 25088;   // 3 KiB CTA tables + 9 * 25 088 B = 228 864 B <= 227 KB per CTA
 

@@ -156,3 +156,34 @@ def test_roundtrip_gpu_encode_gpu_decode(lzb, corpus):
     dec.close()
     assert (status == 1).all() and (dlen == size).all()
     assert np.array_equal(dout.reshape(n, size + 273)[:, :size].reshape(-1), data)
+
+
+def test_encode_8mib_block_max_ratio_settings(lzb, oracle, corpus):
+    """BASELINE config 4 shape: one 8 MiB block, dict 8 MiB, fb 273 (the largest block the encoder takes)."""
+    p = dict(BASE)
+    p.update(dict_size=1 << 23, fb=273)
+    data = corpus.generate(1 << 23, 1, corpus.TEXT, 25, 0).tobytes()
+    got = _gpu_streams(lzb, p, [data])[0]
+    ref = oracle.encode(data, oracle.props(**p), alone=True)
+    assert len(got) == len(ref) and got == ref
+    ok, back = lzb.decode_alone(got)
+    assert ok and back == data
+
+
+def test_encode_block_larger_than_8mib_is_refused(lzb):
+    enc = lzb.Encoder()
+    with pytest.raises(lzb.LzbError) as ei:
+        enc.code_bytes(np.zeros((1 << 23) + 1, dtype=np.uint8))
+    assert ei.value.code == lzb.LZB_E_UNSUPPORTED
+    enc.close()
+
+
+def test_encode_many_tiny_blocks_and_pair_overflow_retry(lzb, oracle, corpus, monkeypatch):
+    blocks = [corpus.generate(200 + (i % 97), 1, i % 4, 26, i).tobytes() for i in range(3000)]
+    got = _gpu_streams(lzb, BASE, blocks)
+    for i in range(0, 3000, 111):
+        assert got[i] == oracle.encode(blocks[i], oracle.props(**BASE), alone=True), i
+    # one pair slot per input byte is not enough for text: the wave is retried with more room
+    monkeypatch.setenv("LZB_PAIR_MUL", "1")
+    text = [corpus.generate(60000, 1, 0, 27, k).tobytes() for k in range(3)]
+    _check(lzb, oracle, BASE, text)
