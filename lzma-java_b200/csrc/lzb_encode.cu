@@ -63,6 +63,7 @@ size_t carve(uint8_t* base, uint32_t wb, uint32_t np, uint32_t hash_stride, uint
     uint32_t* idx = c.take<uint32_t>((size_t)wb * np);
     uint32_t* pairs = c.take<uint32_t>((size_t)wb * pair_cap + 64);   // + slack: the parser prefetches 32 slots blindly
     uint16_t* pairs2 = c.take<uint16_t>((size_t)wb * pair_cap + 64);
+    uint4* long_items = c.take<uint4>((size_t)wb * (np / kLongChain + 1));  // a block has at most n / kLongChain long buckets
     void* opt = c.take<uint8_t>(slots * parse_opt_bytes_per_slot());
     uint16_t* lit = c.take<uint16_t>(lit_slots);
     if (w) {
@@ -76,6 +77,9 @@ size_t carve(uint8_t* base, uint32_t wb, uint32_t np, uint32_t hash_stride, uint
         w->pairs2 = pairs2;
         w->pair_used = pair_used;
         w->overflow = ctl + 1;
+        w->long_count = ctl + 2;
+        w->long_ticket = ctl + 3;
+        w->long_items = long_items;
     }
     if (pa) {
         pa->ticket = ctl;
@@ -154,9 +158,9 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
         w.bt4 = a.bt4;
         e = cudaMemsetAsync(scratch.p, 0, zero_len, st);
         if (e != cudaSuccess) return e;
-        e = launch_mf(w, (uint32_t)a.max_in_len, st);
+        e = launch_mf(w, (uint32_t)a.max_in_len, num_sms, st);
         if (e != cudaSuccess) return e;
-        nl += a.max_in_len ? 2 : 1;
+        nl += a.max_in_len ? 3 : 1;
 
         // did any block run out of pair slots?  (rare: retry the wave with twice the room)
         uint32_t overflow = 0;

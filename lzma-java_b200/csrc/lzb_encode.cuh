@@ -55,7 +55,11 @@ struct MfWave {
                              //                          (Encoder.java:769), a function of the data only
     uint32_t* pair_used;     // [n_blocks]               zeroed; bump allocator
     uint32_t* overflow;      // [1]                      zeroed; set when a block ran out of pair slots
+    uint4* long_items;       // buckets longer than kLongChain: (block, last inserted position, next position, -)
+    uint32_t* long_count;    // [1] zeroed
+    uint32_t* long_ticket;   // [1] zeroed
 };
+constexpr uint32_t kLongChain = 48;  // positions a bucket's thread inserts itself before handing over
 
 struct ParseArgs {
     MfWave mf;               // inputs + match lists of the wave
@@ -80,7 +84,7 @@ struct ParseGeometry {
 };
 
 cudaError_t upload_mf_tables();
-cudaError_t launch_mf(const MfWave& w, uint32_t max_len, cudaStream_t st);
+cudaError_t launch_mf(const MfWave& w, uint32_t max_len, int num_sms, cudaStream_t st);
 cudaError_t launch_parse(const ParseArgs& a, int grid, int warps, cudaStream_t st);
 ParseGeometry parse_geometry(int lc, int lp, int pb, int fb);
 size_t parse_opt_bytes_per_slot();

@@ -128,54 +128,119 @@ __global__ void __launch_bounds__(128) lzb_mf_link_kernel(MfWave w) {
     }
 }
 
+// ---- pieces shared by the two tree kernels ------------------------------------
+struct TreeBlock {
+    const uint8_t* buf;  // buf[pos1] is the byte at 1-based position pos1
+    const uint32_t* prev2;
+    const uint32_t* prev3;
+    const uint32_t* next;
+    uint32_t* son;
+    uint32_t* idx;
+    uint32_t* pairs_out;
+    uint16_t* pairs2_out;
+    uint32_t n;
+    __device__ __forceinline__ TreeBlock(const MfWave& w, uint32_t b) {
+        buf = w.in + w.in_off[b] - 1;
+        prev2 = w.prev2 + (size_t)b * w.np;
+        prev3 = w.prev3 + (size_t)b * w.np;
+        next = w.next + (size_t)b * w.np;
+        son = w.son + (size_t)b * 2 * w.np;
+        idx = w.idx + (size_t)b * w.np;
+        pairs_out = w.pairs + (size_t)b * w.pair_cap;
+        pairs2_out = w.pairs2 + (size_t)b * w.pair_cap;
+        n = (uint32_t)w.in_len[b];
+    }
+};
+
+// hash-2 / hash-3 candidates (BinTree.java:183-208) or the bt2 direct-byte check (:218-226)
+__device__ __forceinline__ void tree_prepairs(const MfWave& w, const TreeBlock& t, uint32_t pos1, uint32_t cur_match,
+                                              uint32_t match_min_pos, uint32_t* pairs, uint32_t& cnt, uint32_t& max_len) {
+    const uint8_t* cur = t.buf + pos1;
+    max_len = 1;  // kStartMaxLen
+    cnt = 0;
+    if (w.bt4) {
+        uint32_t c2 = t.prev2[pos1] & ~kHeadFlag;
+        const uint32_t c3 = t.prev3[pos1];
+        if (c2 > match_min_pos && t.buf[c2] == cur[0]) {
+            max_len = 2;
+            pairs[cnt++] = (2u << kPairDistBits) | (pos1 - c2 - 1);
+        }
+        if (c3 > match_min_pos && t.buf[c3] == cur[0]) {
+            if (c3 == c2) cnt--;
+            max_len = 3;
+            pairs[cnt++] = (3u << kPairDistBits) | (pos1 - c3 - 1);
+            c2 = c3;
+        }
+        if (cnt != 0 && c2 == cur_match) {
+            cnt--;
+            max_len = 1;
+        }
+    } else if (cur_match > match_min_pos && t.buf[cur_match + 2] != cur[2]) {
+        max_len = 2;
+        pairs[cnt++] = (2u << kPairDistBits) | (pos1 - cur_match - 1);
+    }
+}
+
+// write the finished list of a position, with the "match + literal + rep0" continuation of each pair
+// (Encoder.java:766-770 asks for it at every pair boundary; it depends on the data only)
+__device__ __forceinline__ void tree_store_list(const MfWave& w, const TreeBlock& t, uint32_t b, uint32_t pos1, const uint32_t* pairs,
+                                                uint32_t cnt) {
+    uint32_t where = kMfEmpty;
+    if (cnt) {
+        const uint32_t off = atomicAdd(&w.pair_used[b], cnt + 1);
+        if (off + cnt + 1 <= w.pair_cap) {
+            where = off;
+            t.pairs_out[off] = cnt;
+            for (uint32_t i = 0; i < cnt; i++) {
+                t.pairs_out[off + 1 + i] = pairs[i];
+                const uint32_t len = pairs[i] >> kPairDistBits, dist = pairs[i] & kPairDistMask;
+                const uint32_t s1 = pos1 + len + 1;  // 1-based start of the continuation
+                uint32_t lim = s1 <= t.n ? t.n + 1 - s1 : 0;
+                if (lim > (uint32_t)w.fb) lim = (uint32_t)w.fb;
+                const uint8_t* a = t.buf + s1;
+                const uint8_t* c = a - dist - 1;
+                uint32_t k = 0;
+                while (k < lim && a[k] == c[k]) k++;
+                t.pairs2_out[off + 1 + i] = (uint16_t)k;
+            }
+        } else {
+            *w.overflow = 1;
+        }
+    }
+    t.idx[pos1] = where;
+}
+
+// One thread per hash-4 bucket.  A bucket with more than kLongChain positions hands the rest of its
+// chain to lzb_mf_long_kernel, which pipelines the insertions of one chain across a warp.
 __global__ void __launch_bounds__(256) lzb_mf_tree_kernel(MfWave w) {
     const uint32_t b = blockIdx.y;
     const uint32_t n = (uint32_t)w.in_len[b];
     const uint32_t p0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (p0 >= n) return;
-    const uint32_t* prev2 = w.prev2 + (size_t)b * w.np;
     uint32_t pos1 = p0 + 1;
-    if (!(prev2[pos1] & kHeadFlag)) return;  // not the first position of a bucket
+    if (!((w.prev2 + (size_t)b * w.np)[pos1] & kHeadFlag)) return;  // not the first position of a bucket
 
-    const uint8_t* buf = w.in + w.in_off[b] - 1;  // buf[pos1] is the byte at 1-based position pos1
-    const uint32_t* prev3 = w.prev3 + (size_t)b * w.np;
-    const uint32_t* next = w.next + (size_t)b * w.np;
-    uint32_t* son = w.son + (size_t)b * 2 * w.np;
-    uint32_t* idx = w.idx + (size_t)b * w.np;
-    uint32_t* pairs_out = w.pairs + (size_t)b * w.pair_cap;
-    uint16_t* pairs2_out = w.pairs2 + (size_t)b * w.pair_cap;
+    const TreeBlock t(w, b);
+    uint32_t* son = t.son;
     const uint32_t direct = w.bt4 ? 0 : 2;  // kNumHashDirectBytes
 
     uint32_t pairs[kMatchMaxLen];
     uint32_t cur_match = 0;  // the hash-4 head: previous position of this bucket (0 = kEmptyHashValue)
+    uint32_t done = 0;
     while (pos1 != 0) {
-        const uint32_t nxt = next[pos1];
+        if (done == kLongChain) {
+            const uint32_t k = atomicAdd(w.long_count, 1u);
+            w.long_items[k] = make_uint4(b, cur_match, pos1, 0);
+            return;
+        }
+        done++;
+        const uint32_t nxt = t.next[pos1];
         const uint32_t remaining = n - (pos1 - 1);
         const uint32_t len_limit = remaining < (uint32_t)w.fb ? remaining : (uint32_t)w.fb;  // BinTree.java:153-162
         const uint32_t match_min_pos = pos1 > w.cyclic_size ? pos1 - w.cyclic_size : 0;     // :164
-        const uint8_t* cur = buf + pos1;
-        uint32_t max_len = 1, cnt = 0;  // kStartMaxLen
-        if (w.bt4) {  // :183-208
-            uint32_t c2 = prev2[pos1] & ~kHeadFlag;
-            const uint32_t c3 = prev3[pos1];
-            if (c2 > match_min_pos && buf[c2] == cur[0]) {
-                max_len = 2;
-                pairs[cnt++] = (2u << kPairDistBits) | (pos1 - c2 - 1);
-            }
-            if (c3 > match_min_pos && buf[c3] == cur[0]) {
-                if (c3 == c2) cnt--;
-                max_len = 3;
-                pairs[cnt++] = (3u << kPairDistBits) | (pos1 - c3 - 1);
-                c2 = c3;
-            }
-            if (cnt != 0 && c2 == cur_match) {
-                cnt--;
-                max_len = 1;
-            }
-        } else if (cur_match > match_min_pos && buf[cur_match + 2] != cur[2]) {  // :218-226
-            max_len = 2;
-            pairs[cnt++] = (2u << kPairDistBits) | (pos1 - cur_match - 1);
-        }
+        const uint8_t* cur = t.buf + pos1;
+        uint32_t max_len, cnt;
+        tree_prepairs(w, t, pos1, cur_match, match_min_pos, pairs, cnt, max_len);
 
         uint32_t ptr0 = 2 * pos1 + 1, ptr1 = 2 * pos1;
         uint32_t len0 = direct, len1 = direct;
@@ -187,7 +252,7 @@ __global__ void __launch_bounds__(256) lzb_mf_tree_kernel(MfWave w) {
                 son[ptr1] = 0;
                 break;
             }
-            const uint8_t* pby1 = buf + cm;
+            const uint8_t* pby1 = t.buf + cm;
             // both children of the candidate in one 8-byte load, issued together with the first byte
             // compare: one dependent memory round trip per tree level instead of two.  (The slots
             // written below belong to other nodes, never to `cm`, so reading early is safe.)
@@ -218,38 +283,122 @@ __global__ void __launch_bounds__(256) lzb_mf_tree_kernel(MfWave w) {
                 len0 = len;
             }
         }
-
-        uint32_t where = kMfEmpty;
-        if (cnt) {
-            const uint32_t off = atomicAdd(&w.pair_used[b], cnt + 1);
-            if (off + cnt + 1 <= w.pair_cap) {
-                where = off;
-                pairs_out[off] = cnt;
-                for (uint32_t i = 0; i < cnt; i++) {
-                    pairs_out[off + 1 + i] = pairs[i];
-                    // length of the rep0 match that could follow "this match + one literal"
-                    // (Encoder.java:766-770 asks for it at every pair boundary)
-                    const uint32_t len = pairs[i] >> kPairDistBits, dist = pairs[i] & kPairDistMask;
-                    const uint32_t s1 = pos1 + len + 1;  // 1-based start of the continuation
-                    uint32_t lim = s1 <= n ? n + 1 - s1 : 0;
-                    if (lim > (uint32_t)w.fb) lim = (uint32_t)w.fb;
-                    const uint8_t* a = buf + s1;
-                    const uint8_t* b = a - dist - 1;
-                    uint32_t k = 0;
-                    while (k < lim && a[k] == b[k]) k++;
-                    pairs2_out[off + 1 + i] = (uint16_t)k;
-                }
-            } else {
-                *w.overflow = 1;
-            }
-        }
-        idx[pos1] = where;
+        tree_store_list(w, t, b, pos1, pairs, cnt);
         cur_match = pos1;
         pos1 = nxt;
     }
 }
 
-cudaError_t launch_mf(const MfWave& w, uint32_t max_len, cudaStream_t st) {
+// Long buckets: one warp per chain, 32 consecutive insertions of the chain in flight.
+// The insertion of a position rewrites links strictly top-down: at any time it owns exactly two
+// "pending" slots (the reference's ptr0 / ptr1), every link above them is final, everything below
+// is untouched.  Pending slots hold kPending; a later insertion that needs such a link waits (it
+// retries in the next round), so it can never overtake an earlier one, and each insertion sees
+// exactly the tree the sequential order would have shown it.
+constexpr uint32_t kPending = 0xFFFFFFFFu;
+
+__global__ void __launch_bounds__(256) lzb_mf_long_kernel(MfWave w) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t direct = w.bt4 ? 0 : 2;
+    uint32_t pairs[kMatchMaxLen];
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(w.long_ticket, 1u);
+        item = __shfl_sync(kFull, item, 0);
+        if (item >= *w.long_count) break;
+        const uint4 it = w.long_items[item];
+        const uint32_t b = it.x;
+        const TreeBlock t(w, b);
+        volatile uint32_t* son = t.son;
+        uint32_t last = it.y, walk = it.z;
+        while (walk != 0) {
+            // the next (up to) 32 positions of the chain, one per lane
+            uint32_t pos1 = 0;
+            for (int k = 0; k < 32; k++) {
+                if (lane == k) pos1 = walk;
+                if (walk) walk = t.next[walk];
+            }
+            const bool active = pos1 != 0;
+            uint32_t root = __shfl_up_sync(kFull, pos1, 1);
+            if (lane == 0) root = last;
+            const unsigned am = __ballot_sync(kFull, active);
+            last = __shfl_sync(kFull, pos1, 31 - __clz(am));
+
+            uint32_t len_limit = 0, match_min_pos = 0, max_len = 1, cnt = 0;
+            uint32_t ptr0 = 0, ptr1 = 0, len0 = direct, len1 = direct, cm = root;
+            int32_t count = w.cut;
+            bool done = !active;
+            if (active) {
+                const uint32_t remaining = t.n - (pos1 - 1);
+                len_limit = remaining < (uint32_t)w.fb ? remaining : (uint32_t)w.fb;
+                match_min_pos = pos1 > w.cyclic_size ? pos1 - w.cyclic_size : 0;
+                tree_prepairs(w, t, pos1, root, match_min_pos, pairs, cnt, max_len);
+                ptr0 = 2 * pos1 + 1;
+                ptr1 = 2 * pos1;
+                son[ptr0] = kPending;
+                son[ptr1] = kPending;
+            }
+            __syncwarp();
+            const uint8_t* cur = t.buf + pos1;
+            // state of the compare with the current candidate (kept across retries)
+            bool have_cmp = false;
+            uint32_t len = 0;
+            while (__any_sync(kFull, !done)) {
+                if (!done) {
+                    if (cm <= match_min_pos || count == 0) {  // :231-235
+                        son[ptr0] = 0;
+                        son[ptr1] = 0;
+                        done = true;
+                    } else {
+                        const uint8_t* pby1 = t.buf + cm;
+                        if (!have_cmp) {
+                            len = len0 < len1 ? len0 : len1;
+                            if (pby1[len] == cur[len]) {
+                                while (++len != len_limit)
+                                    if (pby1[len] != cur[len]) break;
+                            }
+                            have_cmp = true;
+                        }
+                        const bool full = len == len_limit && max_len < len;  // :249-256 ends the insertion
+                        const bool right = !full && pby1[len] < cur[len];
+                        const uint32_t kx = son[2 * cm], ky = son[2 * cm + 1];
+                        const bool ready = full ? (kx != kPending && ky != kPending) : (right ? ky != kPending : kx != kPending);
+                        if (ready) {
+                            count--;
+                            have_cmp = false;
+                            if (max_len < len) {
+                                max_len = len;
+                                pairs[cnt++] = (len << kPairDistBits) | (pos1 - cm - 1);
+                            }
+                            if (full) {
+                                son[ptr1] = kx;
+                                son[ptr0] = ky;
+                                done = true;
+                            } else if (right) {
+                                son[ptr1] = cm;
+                                ptr1 = 2 * cm + 1;
+                                son[ptr1] = kPending;
+                                cm = ky;
+                                len1 = len;
+                            } else {
+                                son[ptr0] = cm;
+                                ptr0 = 2 * cm;
+                                son[ptr0] = kPending;
+                                cm = kx;
+                                len0 = len;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            if (active) tree_store_list(w, t, b, pos1, pairs, cnt);
+            __syncwarp();
+        }
+    }
+}
+
+cudaError_t launch_mf(const MfWave& w, uint32_t max_len, int num_sms, cudaStream_t st) {
     if (w.n_blocks == 0) return cudaSuccess;
     const uint32_t warps_per_cta = 4;
     lzb_mf_link_kernel<<<(w.n_blocks + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, st>>>(w);
@@ -258,6 +407,9 @@ cudaError_t launch_mf(const MfWave& w, uint32_t max_len, cudaStream_t st) {
     if (max_len == 0) return cudaSuccess;
     dim3 grid((max_len + 255) / 256, w.n_blocks);
     lzb_mf_tree_kernel<<<grid, 256, 0, st>>>(w);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    lzb_mf_long_kernel<<<num_sms * 8, 256, 0, st>>>(w);
     return cudaGetLastError();
 }
 
