@@ -20,7 +20,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "liblzma_b200.so")
+SO_PATH = os.environ.get("LZB_SO") or os.path.join(_HERE, "liblzma_b200.so")  # LZB_SO: A/B builds of the same ABI
 
 LZB_OK = 1
 LZB_FALSE = 0
