@@ -65,7 +65,51 @@ struct lzb_dec {
     DevBuf lit;      // spilled literal models
     DevBuf d_in, d_out, d_meta;
     PinBuf h_meta;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-buffer batches overlap transfers with the kernel
 };
+
+namespace {
+
+// literal-model size (16-bit slots) a stream needs outside shared memory, 0 if its model fits
+// (the host-side twin of lzb_decode_scan_headers)
+uint32_t spill_slots(const uint8_t* stream, uint64_t len) {
+    if (len < LZB_HEADER_SIZE) return 0;
+    const uint32_t v = stream[0];
+    const int lc = v % 9, rem = v / 9, lp = rem % 5, pb = rem / 5;
+    if (pb > 4) return 0;
+    const lzb::ModelLayout L = lzb::make_layout(lc, lp, pb);
+    return (size_t)(L.n_fixed + L.n_literal) * 2 > lzb::kDecSliceBytes ? (uint32_t)L.n_literal : 0;
+}
+
+// enqueue the decode kernel for n streams (no header scan, no synchronisation)
+int dec_enqueue(lzb_dec* d, const uint8_t* d_in, const uint64_t* d_in_off, const uint64_t* d_in_len, uint32_t n,
+                uint8_t* d_out, const uint64_t* d_out_off, const uint64_t* d_out_cap, uint64_t* d_out_len,
+                int32_t* d_status, uint32_t max_spill, uint32_t* ticket, cudaStream_t st) {
+    lzb::DecodeArgs a;
+    a.in = d_in;
+    a.in_off = d_in_off;
+    a.in_len = d_in_len;
+    a.out = d_out;
+    a.out_off = d_out_off;
+    a.out_cap = d_out_cap;
+    a.out_len = d_out_len;
+    a.status = d_status;
+    a.n = n;
+    a.ticket = ticket;
+    a.lit_scratch = nullptr;
+    a.lit_stride = 0;
+    if (max_spill) {
+        a.lit_stride = max_spill;
+        const size_t slots = (size_t)d->num_sms * lzb::kDecMaxWarps;
+        CUDA_TRY(d->lit.reserve(slots * a.lit_stride * sizeof(uint16_t)));
+        a.lit_scratch = (uint16_t*)d->lit.p;
+    }
+    CUDA_TRY(lzb::launch_decode(a, max_spill == 0, d->num_sms, st, nullptr, nullptr));
+    add_launches(1);
+    return LZB_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -116,6 +160,8 @@ void lzb_dec_destroy(lzb_dec* d) {
     d->d_meta.release();
     d->h_meta.release();
     if (d->stream) cudaStreamDestroy(d->stream);
+    if (d->copy_in) cudaStreamDestroy(d->copy_in);
+    if (d->copy_out) cudaStreamDestroy(d->copy_out);
     delete d;
 }
 
@@ -153,28 +199,7 @@ int lzb_dec_code_batch_device(lzb_dec* d, const uint8_t* d_in, const uint64_t* d
     CUDA_TRY(cudaMemcpyAsync(&max_spill, ctrl + 1, sizeof max_spill, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
 
-    lzb::DecodeArgs a;
-    a.in = d_in;
-    a.in_off = d_in_off;
-    a.in_len = d_in_len;
-    a.out = d_out;
-    a.out_off = d_out_off;
-    a.out_cap = d_out_cap;
-    a.out_len = d_out_len;
-    a.status = d_status;
-    a.n = n;
-    a.ticket = ctrl;
-    a.lit_scratch = nullptr;
-    a.lit_stride = 0;
-    if (max_spill) {
-        a.lit_stride = max_spill;
-        const size_t slots = (size_t)d->num_sms * lzb::kDecMaxWarps;
-        CUDA_TRY(d->lit.reserve(slots * a.lit_stride * sizeof(uint16_t)));
-        a.lit_scratch = (uint16_t*)d->lit.p;
-    }
-    CUDA_TRY(lzb::launch_decode(a, max_spill == 0, d->num_sms, st, nullptr, nullptr));
-    add_launches(1);
-    return LZB_OK;
+    return dec_enqueue(d, d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_cap, d_out_len, d_status, max_spill, ctrl, st);
 }
 
 int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len, uint32_t n,
@@ -186,9 +211,10 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
         return fail(LZB_E_ARG, "null argument");
     CUDA_TRY(cudaSetDevice(d->device));
     cudaStream_t st = d->stream;
+    if (!d->copy_in) CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_in, cudaStreamNonBlocking));
+    if (!d->copy_out) CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_out, cudaStreamNonBlocking));
 
-    // Device images keep the caller's layout: one copy per direction over the
-    // smallest covering span.
+    // Device images keep the caller's layout (offsets relative to the smallest covering span).
     const Span si = span_of(in_off, in_len, n);
     const Span so = span_of(out_off, out_cap, n);
     const size_t in_bytes = si.hi - si.lo, out_bytes = so.hi - so.lo;
@@ -199,24 +225,84 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
     CUDA_TRY(d->d_meta.reserve(meta_bytes));
     CUDA_TRY(d->h_meta.reserve(meta_bytes));
     uint64_t* hm = (uint64_t*)d->h_meta.p;
+    uint32_t max_spill = 0;
     for (uint32_t i = 0; i < n; i++) {
         hm[i] = in_off[i] - si.lo;
         hm[n + i] = in_len[i];
         hm[2 * (size_t)n + i] = out_off[i] - so.lo;
         hm[3 * (size_t)n + i] = out_cap[i];
+        const uint32_t sp = spill_slots(in + in_off[i], in_len[i]);
+        if (sp > max_spill) max_spill = sp;
     }
     uint64_t* dm = (uint64_t*)d->d_meta.p;
-    CUDA_TRY(cudaMemcpyAsync(dm, hm, (size_t)n * 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d->d_in.p, in + si.lo, in_bytes, cudaMemcpyHostToDevice, st));
+    uint8_t* d_in = (uint8_t*)d->d_in.p;
+    uint8_t* d_out = (uint8_t*)d->d_out.p;
 
-    int rc = lzb_dec_code_batch_device(d, (const uint8_t*)d->d_in.p, dm, dm + n, n, (uint8_t*)d->d_out.p,
-                                       dm + 2 * (size_t)n, dm + 3 * (size_t)n, dm + 4 * (size_t)n,
-                                       (int32_t*)(dm + 5 * (size_t)n), st);
+    // One kernel launch decodes one "wave" (num_sms x 15 resident streams).  Launching wave by wave
+    // costs nothing (the waves would run back to back inside one launch anyway) and lets the
+    // input copy of wave k+1 and the output copy of wave k-1 overlap the kernel of wave k.
+    const uint32_t wave = (uint32_t)d->num_sms * lzb::kDecMaxWarps;
+    uint32_t n_chunks = (n + wave - 1) / wave;
+    if (n_chunks > 16) n_chunks = 16;
+    std::vector<uint32_t> first(n_chunks + 1);
+    std::vector<Span> cin(n_chunks), cout(n_chunks);
+    for (uint32_t c = 0; c <= n_chunks; c++) first[c] = (uint32_t)((uint64_t)n * c / n_chunks);
+    bool ordered = true;
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        cin[c] = span_of(in_off + first[c], in_len + first[c], first[c + 1] - first[c]);
+        cout[c] = span_of(out_off + first[c], out_cap + first[c], first[c + 1] - first[c]);
+        if (c && (cin[c].lo < cin[c - 1].hi || cout[c].lo < cout[c - 1].hi)) ordered = false;
+    }
+    if (!ordered) {  // interleaved layout: one chunk, copies around the kernel
+        n_chunks = 1;
+        first[1] = n;
+        cin[0] = si;
+        cout[0] = so;
+    }
+    CUDA_TRY(d->ctrl.reserve(64 * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemsetAsync(d->ctrl.p, 0, 64 * sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemcpyAsync(dm, hm, (size_t)n * 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    cudaEvent_t ready, ev_in[16], ev_k[16];
+    uint32_t n_events = 0;
+    CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    cudaEventRecord(ready, st);
+    cudaStreamWaitEvent(d->copy_in, ready, 0);  // the device images are free once earlier work on `st` is done
+    cudaStreamWaitEvent(d->copy_out, ready, 0);
+    int rc = LZB_OK;
+    cudaError_t err = cudaSuccess;
+    for (uint32_t c = 0; c < n_chunks && rc == LZB_OK && err == cudaSuccess; c++) {
+        const uint32_t s0 = first[c], cnt = first[c + 1] - s0;
+        cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_k[c], cudaEventDisableTiming);
+        n_events = c + 1;
+        if (cin[c].hi > cin[c].lo)
+            err = cudaMemcpyAsync(d_in + (cin[c].lo - si.lo), in + cin[c].lo, cin[c].hi - cin[c].lo, cudaMemcpyHostToDevice, d->copy_in);
+        if (err != cudaSuccess) break;
+        cudaEventRecord(ev_in[c], d->copy_in);
+        cudaStreamWaitEvent(st, ev_in[c], 0);
+        rc = dec_enqueue(d, d_in, dm + s0, dm + n + s0, cnt, d_out, dm + 2 * (size_t)n + s0, dm + 3 * (size_t)n + s0,
+                         dm + 4 * (size_t)n + s0, (int32_t*)(dm + 5 * (size_t)n) + s0, max_spill, (uint32_t*)d->ctrl.p + c, st);
+        if (rc != LZB_OK) break;
+        cudaEventRecord(ev_k[c], st);
+        cudaStreamWaitEvent(d->copy_out, ev_k[c], 0);
+        if (cout[c].hi > cout[c].lo)
+            err = cudaMemcpyAsync(out + cout[c].lo, d_out + (cout[c].lo - so.lo), cout[c].hi - cout[c].lo, cudaMemcpyDeviceToHost,
+                                  d->copy_out);
+    }
+    if (rc == LZB_OK && err == cudaSuccess)
+        err = cudaMemcpyAsync(hm + 4 * (size_t)n, dm + 4 * (size_t)n, (size_t)n * (sizeof(uint64_t) + sizeof(int32_t)),
+                              cudaMemcpyDeviceToHost, st);
+    const cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(d->copy_out), e3 = cudaStreamSynchronize(d->copy_in);
+    cudaEventDestroy(ready);
+    for (uint32_t c = 0; c < n_events; c++) {
+        cudaEventDestroy(ev_in[c]);
+        cudaEventDestroy(ev_k[c]);
+    }
     if (rc != LZB_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(hm + 4 * (size_t)n, dm + 4 * (size_t)n, (size_t)n * (sizeof(uint64_t) + sizeof(int32_t)),
-                             cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(out + so.lo, d->d_out.p, out_bytes, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(err);
+    CUDA_TRY(e1);
+    CUDA_TRY(e2);
+    CUDA_TRY(e3);
     memcpy(out_len, hm + 4 * (size_t)n, (size_t)n * sizeof(uint64_t));
     memcpy(status, hm + 5 * (size_t)n, (size_t)n * sizeof(int32_t));
     return LZB_OK;
