@@ -492,10 +492,7 @@ struct Enc {
             if (match_mode && (((match_byte ^ symbol) & 0xFF) >> (i + 1)) == 0) index += (1 + ((match_byte >> i) & 1)) << 8;
             price = price_bit(probs[index], bit);
         }
-        price += __shfl_xor_sync(kFull, price, 1);
-        price += __shfl_xor_sync(kFull, price, 2);
-        price += __shfl_xor_sync(kFull, price, 4);
-        return __shfl_sync(kFull, price, 0);
+        return __reduce_add_sync(kFull, price);  // one REDUX instead of a four-shuffle tree
     }
 
     // ---- rep / match prices (Encoder.java:296-333) ----
