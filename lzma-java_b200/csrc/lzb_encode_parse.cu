@@ -133,6 +133,25 @@ struct RangeEnc {
 #pragma unroll 1
         for (int i = 0; i < 5; i++) shift_low();
     }
+    // fold one decision (old probability | bit << 16 | direct << 17) into low / range
+    __device__ __forceinline__ void step(uint32_t e) {
+        if (e & 0x20000u) {
+            range >>= 1;
+            if (e & 0x10000u) low += range;
+        } else {
+            const uint32_t bound = (range >> kNumBitModelTotalBits) * (e & 0xFFFFu);
+            if (e & 0x10000u) {
+                low += bound;
+                range -= bound;
+            } else {
+                range = bound;
+            }
+        }
+        if (range < kTopValue) {
+            range <<= 8;
+            shift_low();
+        }
+    }
     // Encode `cnt` (<= 32) decisions.  Lane k < cnt passes its decision: `prob` (ignored for a
     // direct bit), `bit`, `direct`.  RangeEncoder.encode :38-54 / encodeDirectBits :56-67.
     __device__ __forceinline__ void batch(int cnt, uint16_t* prob, uint32_t bit, bool direct) {
@@ -142,25 +161,18 @@ struct RangeEnc {
             *prob = (uint16_t)(bit ? p - (p >> kNumMoveBits) : p + ((kBitModelTotal - p) >> kNumMoveBits));
         }
         const uint32_t w = p | (bit << 16) | ((uint32_t)direct << 17);
+        // four decisions per round: the shuffles do not depend on the coder state, so fetching them
+        // together takes their latency off the serial low/range chain
 #pragma unroll 1
-        for (int k = 0; k < cnt; k++) {
-            const uint32_t e = __shfl_sync(kFull, w, k);
-            if (e & 0x20000u) {
-                range >>= 1;
-                if (e & 0x10000u) low += range;
-            } else {
-                const uint32_t bound = (range >> kNumBitModelTotalBits) * (e & 0xFFFFu);
-                if (e & 0x10000u) {
-                    low += bound;
-                    range -= bound;
-                } else {
-                    range = bound;
-                }
-            }
-            if (range < kTopValue) {
-                range <<= 8;
-                shift_low();
-            }
+        for (int k = 0; k < cnt; k += 4) {
+            const uint32_t e0 = __shfl_sync(kFull, w, k);
+            const uint32_t e1 = __shfl_sync(kFull, w, (k + 1) & 31);
+            const uint32_t e2 = __shfl_sync(kFull, w, (k + 2) & 31);
+            const uint32_t e3 = __shfl_sync(kFull, w, (k + 3) & 31);
+            step(e0);
+            if (k + 1 < cnt) step(e1);
+            if (k + 2 < cnt) step(e2);
+            if (k + 3 < cnt) step(e3);
         }
         __syncwarp();
     }
@@ -972,9 +984,10 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
             __syncwarp();
         }
 
-        // ---- reps (:669-735)
+        // ---- reps (:669-735); most positions have no rep of length >= 2 at all
+        const bool any_rep = len_test[0] >= 2 || len_test[1] >= 2 || len_test[2] >= 2 || len_test[3] >= 2;
 #pragma unroll 1
-        for (int rep_index = 0; rep_index < kNumRepDistances; rep_index++) {
+        for (int rep_index = 0; any_rep && rep_index < kNumRepDistances; rep_index++) {
             const int lt = sel4(len_test, rep_index);
             if (lt < 2) continue;
             const uint32_t rp = rep_match_price + pure_rep_price(rep_index, st, pos_state);
