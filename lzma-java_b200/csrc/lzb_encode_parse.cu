@@ -239,6 +239,13 @@ template <typename T>
 __device__ __forceinline__ T sel4(const T (&a)[4], int i) {
     return i == 0 ? a[0] : (i == 1 ? a[1] : (i == 2 ? a[2] : a[3]));
 }
+template <typename T>
+__device__ __forceinline__ void set4(T (&a)[4], int i, T v) {
+    if (i == 0) a[0] = v;
+    if (i == 1) a[1] = v;
+    if (i == 2) a[2] = v;
+    if (i == 3) a[3] = v;
+}
 
 // ---- everything one stream needs (identical in every lane unless noted) -----
 struct Enc {
@@ -344,16 +351,29 @@ struct Enc {
         return warp_match_len(data, n, lane, s, distance, limit);
     }
 
-    // run of set bits in a 32-byte equality bitmap starting at bit `start`, continued in memory
-    // when it runs off the bitmap; `base` is the absolute position of bit 0, capped at `limit`
-    __device__ __forceinline__ int eq_run(unsigned e, int start, uint32_t base, uint32_t distance, int limit) const {
+    // Run of set bits in a 32-byte equality bitmap starting at bit `start`, capped at `limit`.
+    // Pure bit arithmetic: when the run reaches the end of the bitmap with the limit not exhausted,
+    // `more` is set and the caller continues in memory (eq_more) -- rare, and kept out of the hot path
+    // so that the DP step stays small in the instruction cache.
+    __device__ __forceinline__ int eq_fast(unsigned e, int start, int limit, bool& more) const {
+        more = false;
         if (limit <= 0) return 0;
-        if (start >= 32) return match_len_abs(base + start, distance, limit);
+        if (start >= 32) {
+            more = true;
+            return 0;
+        }
         const int room = 32 - start;
         const unsigned w = ~(e >> start);
         const int run = w ? __ffs(w) - 1 : 32;  // for start > 0 the top `start` bits of w are set, so run <= room
-        if (run >= room && limit > room) return room + match_len_abs(base + 32, distance, limit - room);
+        if (run >= room && limit > room) {
+            more = true;
+            return room;
+        }
         return run < limit ? run : limit;
+    }
+    // continuation of eq_fast: `base` = absolute position of bit 0 of the bitmap
+    __device__ __forceinline__ int eq_more(int fast, int start, uint32_t base, uint32_t distance, int limit) const {
+        return fast + match_len_abs(base + start + fast, distance, limit - fast);
     }
 
     // ---- match list ----
@@ -383,21 +403,30 @@ struct Enc {
 
     __device__ __forceinline__ int read_match_distances() {  // Encoder.java:275-287
         __syncwarp();  // everyone is done with the previous list
-        if (pf_pos != m) prefetch_list(m);
-        const int cnt = (int)pf_cnt;
-        if (lane < cnt) {
-            md[lane] = pf_pair;
-            md2[lane] = (uint16_t)pf_l2;
-        }
-        #pragma unroll 1
-        for (int i = 32 + lane; i < cnt; i += 32) {
-            md[i] = pairs[pf_from + 1 + i];
-            md2[i] = pairs2[pf_from + 1 + i];
+        int cnt = 0;
+        // one inlined copy of prefetch_list: round 1 fetches the wanted list if the prefetch missed
+        // (after a Skip), the last round prefetches the next position
+#pragma unroll 1
+        for (bool consumed = false;;) {
+            if (!consumed && pf_pos == m) {
+                cnt = (int)pf_cnt;
+                if (lane < cnt) {
+                    md[lane] = pf_pair;
+                    md2[lane] = (uint16_t)pf_l2;
+                }
+#pragma unroll 1
+                for (int i = 32 + lane; i < cnt; i += 32) {
+                    md[i] = pairs[pf_from + 1 + i];
+                    md2[i] = pairs2[pf_from + 1 + i];
+                }
+                m++;  // fillMatches advanced the window
+                consumed = true;
+            }
+            prefetch_list(m);
+            if (consumed) break;
         }
         __syncwarp();
         num_pairs = cnt;
-        m++;  // fillMatches advanced the window
-        prefetch_list(m);
         int length = 0;
         if (cnt > 0) {
             length = md_len(cnt - 1);
@@ -700,10 +729,18 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
         if (in_range) b_byte[i] = data[c + lane - reps[i] - 1];
     }
     int rep_max_index = 0;
+    {
+        bool more[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        eq[i] = __ballot_sync(kFull, in_range && a_byte == b_byte[i]);
-        rep_lens[i] = (uint32_t)eq_run(eq[i], 0, c, reps[i], kMatchMaxLen);
+        for (int i = 0; i < 4; i++) {
+            eq[i] = __ballot_sync(kFull, in_range && a_byte == b_byte[i]);
+            rep_lens[i] = (uint32_t)eq_fast(eq[i], 0, kMatchMaxLen, more[i]);
+        }
+        if (more[0] || more[1] || more[2] || more[3]) {
+#pragma unroll 1
+            for (int i = 0; i < 4; i++)
+                if (sel4(more, i)) set4(rep_lens, i, (uint32_t)eq_more((int)sel4(rep_lens, i), 0, c, sel4(reps, i), kMatchMaxLen));
+        }
     }
     uint32_t rep_max_len = rep_lens[0];  // first index of the maximum (:396-398)
 #pragma unroll
@@ -926,23 +963,45 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
         // ---- rep lengths and every continuation length, then one extension of the node range
         int len_test[4], len_test2[4];
         int need = len_end;
+        {
+            bool more[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            len_test[i] = eq_run(eq[i], 0, c, reps[i], num_avail);
-            len_test2[i] = 0;
-            if (len_test[i] >= 2) {
-                if (cur + len_test[i] > need) need = cur + len_test[i];
-                if (len_test[i] < num_avail_full) {
-                    const int t = num_avail_full - 1 - len_test[i] < fb ? num_avail_full - 1 - len_test[i] : fb;
-                    len_test2[i] = eq_run(eq[i], len_test[i] + 1, c, reps[i], t);
-                    if (len_test2[i] >= 2 && cur + len_test[i] + 1 + len_test2[i] > need) need = cur + len_test[i] + 1 + len_test2[i];
+            for (int i = 0; i < 4; i++) len_test[i] = eq_fast(eq[i], 0, num_avail, more[i]);
+            if (more[0] || more[1] || more[2] || more[3]) {
+#pragma unroll 1
+                for (int i = 0; i < 4; i++)
+                    if (sel4(more, i)) set4(len_test, i, eq_more(sel4(len_test, i), 0, c, sel4(reps, i), num_avail));
+            }
+            int lim2[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                len_test2[i] = 0;
+                more[i] = false;
+                lim2[i] = 0;
+                if (len_test[i] >= 2) {
+                    if (cur + len_test[i] > need) need = cur + len_test[i];
+                    if (len_test[i] < num_avail_full) {
+                        lim2[i] = num_avail_full - 1 - len_test[i] < fb ? num_avail_full - 1 - len_test[i] : fb;
+                        len_test2[i] = eq_fast(eq[i], len_test[i] + 1, lim2[i], more[i]);
+                    }
                 }
             }
+            if (more[0] || more[1] || more[2] || more[3]) {
+#pragma unroll 1
+                for (int i = 0; i < 4; i++)
+                    if (sel4(more, i))
+                        set4(len_test2, i, eq_more(sel4(len_test2, i), sel4(len_test, i) + 1, c, sel4(reps, i), sel4(lim2, i)));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (len_test2[i] >= 2 && cur + len_test[i] + 1 + len_test2[i] > need) need = cur + len_test[i] + 1 + len_test2[i];
         }
         int lit_rep0_len = 0;
         if (!next_is_char && match_byte != current_byte) {  // :637-641
             const int t = num_avail_full - 1 < fb ? num_avail_full - 1 : fb;
-            lit_rep0_len = eq_run(eq[0], 1, c, reps[0], t);
+            bool more0;
+            lit_rep0_len = eq_fast(eq[0], 1, t, more0);
+            if (more0) lit_rep0_len = eq_more(lit_rep0_len, 1, c, reps[0], t);
             if (lit_rep0_len >= 2 && cur + 1 + lit_rep0_len > need) need = cur + 1 + lit_rep0_len;
         }
         const int start_len = len_test[0] >= 2 ? len_test[0] + 1 : 2;  // :667, :691-693
