@@ -161,19 +161,11 @@ struct RangeEnc {
             *prob = (uint16_t)(bit ? p - (p >> kNumMoveBits) : p + ((kBitModelTotal - p) >> kNumMoveBits));
         }
         const uint32_t w = p | (bit << 16) | ((uint32_t)direct << 17);
-        // four decisions per round: the shuffles do not depend on the coder state, so fetching them
-        // together takes their latency off the serial low/range chain
+        // one rolled loop, one copy of the coder step: the emission code is executed by every warp
+        // of the SM at different times, and unrolling it (x4, shuffles hoisted) cost more in
+        // instruction-cache misses at 7-8 streams per SM than the shuffle latency it hid
 #pragma unroll 1
-        for (int k = 0; k < cnt; k += 4) {
-            const uint32_t e0 = __shfl_sync(kFull, w, k);
-            const uint32_t e1 = __shfl_sync(kFull, w, (k + 1) & 31);
-            const uint32_t e2 = __shfl_sync(kFull, w, (k + 2) & 31);
-            const uint32_t e3 = __shfl_sync(kFull, w, (k + 3) & 31);
-            step(e0);
-            if (k + 1 < cnt) step(e1);
-            if (k + 2 < cnt) step(e2);
-            if (k + 3 < cnt) step(e3);
-        }
+        for (int k = 0; k < cnt; k++) step(__shfl_sync(kFull, w, k));
         __syncwarp();
     }
 };
