@@ -13,7 +13,8 @@
 //     one-byte input lookahead in registers;
 //   * matches are copied by all 32 lanes: out[pos+k] = out[pos-d+(k mod d)],
 //     which is order-free even when the match overlaps itself; the output
-//     buffer doubles as the dictionary window (block <= dictionary);
+//     buffer doubles as the dictionary window (a distance never exceeds the
+//     position, and the reference's rep0 >= dictionary check is kept);
 //   * the lane that loads index k = len also supplies the next match byte,
 //     the lane of k = len-1 the new previous byte, so lane 0 never re-reads
 //     global memory after a match.
@@ -25,7 +26,7 @@ namespace lzb {
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 // Range decoder state of one stream, in lane 0's registers.  The kernel is
-// issue-bound (profiles/: ~75 % of issue slots busy with 15 streams per SM), so
+// issue-bound (profiles/: 63-75 % of issue slots busy with 15 streams per SM), so
 // the one thing that matters is the instruction count of a bit decode.  `bit_s`
 // is written in PTX against a shared-memory byte address: 13 instructions
 // (LDS, SHF, IMAD, ISETP, IADD, SEL, @IADD, SEL, IADD, SHF, IADD, STS, SEL).

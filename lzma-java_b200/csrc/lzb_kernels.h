@@ -61,8 +61,7 @@ struct EncScratch {
 };
 
 constexpr uint64_t kEncMaxBlockBytes = 1ull << 23;  // match pairs pack len << 23 | distance
-constexpr int kEncMaxWarps = 9;            // parser streams resident per SM
-constexpr size_t kEncSliceBytes = 25088;   // 3 KiB CTA tables + 9 * 25 088 B = 228 864 B <= 227 KB per CTA
+constexpr int kEncMaxWarps = 9;            // upper bound of parser streams resident per SM (shared memory decides, see parse_geometry)
 
 // Enqueue the whole encode pipeline for the batch on `st`.
 cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cudaStream_t st, int* launches);
