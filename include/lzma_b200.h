@@ -123,6 +123,16 @@ int lzb_enc_code_batch_device(lzb_enc *e, const uint8_t *d_in,
                               const uint64_t *d_out_cap, uint64_t *d_out_len,
                               int32_t with_header13, void *cuda_stream);
 
+/* Trace tap of the match finder (BinTree.fillMatches0 / Skip, BinTree.java:152-356; the
+ * machine-readable twin of the reference's FINE log, BinTree.java:139-150): for every position p
+ * of one block, counts[p] = number of (length, distance) pairs the reference's match finder
+ * yields there -- Skip()ped positions included -- and the pairs themselves, concatenated in
+ * position order as pairs[2k] = length, pairs[2k+1] = distance (= back - 1).  *pairs_used =
+ * total number of pairs.  HOST pointers.  For parity tests and debugging, not a hot path. */
+int lzb_enc_trace_matches(lzb_enc *e, const uint8_t *in, uint64_t in_len,
+                          uint32_t *counts, uint32_t *pairs, uint64_t pairs_cap,
+                          uint64_t *pairs_used);
+
 /* ---- Decoder (Decoder.java) -------------------------------------------- */
 
 /* new Decoder() (Decoder.java:154-158) bound to CUDA device `device`. */

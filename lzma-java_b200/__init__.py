@@ -54,6 +54,7 @@ ABI = [
     ("lzb_enc_code_batch", C.c_int, [_vp, _u8p, _u64p, _u64p, C.c_uint32, _u8p, _u64p, _u64p, _u64p, C.c_int32]),
     ("lzb_enc_code_batch_device", C.c_int,
      [_vp, _u8p, _u64p, _u64p, C.c_uint32, C.c_uint64, _u8p, _u64p, _u64p, _u64p, C.c_int32, _vp]),
+    ("lzb_enc_trace_matches", C.c_int, [_vp, _u8p, C.c_uint64, _vp, _vp, C.c_uint64, _u64p]),
     ("lzb_dec_create", C.c_void_p, [C.c_int]),
     ("lzb_dec_destroy", None, [_vp]),
     ("lzb_dec_set_decoder_properties", C.c_int, [_vp, _u8p, C.c_uint32]),
@@ -179,6 +180,19 @@ class Encoder:
         if rc != 1:
             raise LzbError(rc, "encode failed")
         return out[: n.value].tobytes()
+
+    def trace_matches(self, data):
+        """Match-finder trace tap -> (counts[n], pairs[k, 2]) with pairs as (length, distance)."""
+        a = _u8(data)
+        counts = np.zeros(max(a.size, 1), dtype=np.uint32)
+        cap = max(1024, 16 * a.size)
+        pairs = np.zeros(2 * cap, dtype=np.uint32)
+        used = C.c_uint64(0)
+        rc = _check(lib().lzb_enc_trace_matches(self._h, a.ctypes.data, a.size, counts.ctypes.data, pairs.ctypes.data, cap,
+                                                C.byref(used)))
+        if rc != 1:
+            raise LzbError(rc, "trace failed")
+        return counts[: a.size], pairs[: 2 * used.value].reshape(-1, 2)
 
     def code_batch(self, in_arr, in_off, in_len, with_header=True):
         """n independent streams from host memory -> (out, out_off, out_len)."""

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "lzb_common.cuh"
 #include "lzb_kernels.h"
@@ -188,6 +189,63 @@ int lzb_enc_code_batch(lzb_enc* e, const uint8_t* in, const uint64_t* in_off, co
             return fail(LZB_E_CAPACITY, "block %u: output capacity %llu too small", i, (unsigned long long)out_cap[i]);
         }
     return LZB_OK;
+}
+
+int lzb_enc_trace_matches(lzb_enc* e, const uint8_t* in, uint64_t in_len, uint32_t* counts, uint32_t* pairs,
+                          uint64_t pairs_cap, uint64_t* pairs_used) {
+    if (!e) return fail(LZB_E_ARG, "null handle");
+    if (pairs_used) *pairs_used = 0;
+    if (in_len == 0) return LZB_OK;
+    if (!in || !counts || (!pairs && pairs_cap)) return fail(LZB_E_ARG, "null argument");
+    if (in_len > lzb::kEncMaxBlockBytes) return fail(LZB_E_UNSUPPORTED, "block of %llu bytes is too large", (unsigned long long)in_len);
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    CUDA_TRY(e->d_in.reserve(in_len + 16));
+    CUDA_TRY(e->d_meta.reserve(2 * sizeof(uint64_t)));
+    const uint64_t meta[2] = {0, in_len};
+    CUDA_TRY(cudaMemcpyAsync(e->d_meta.p, meta, sizeof meta, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_in.p, in, in_len, cudaMemcpyHostToDevice, st));
+    lzb::EncodeArgs a = {};
+    a.in = (const uint8_t*)e->d_in.p;
+    a.in_off = (const uint64_t*)e->d_meta.p;
+    a.in_len = (const uint64_t*)e->d_meta.p + 1;
+    a.n = 1;
+    a.max_in_len = in_len;
+    a.dict_size = e->dict_size;
+    a.fb = e->fb;
+    a.bt4 = e->mf != 0;
+    a.lc = e->lc;
+    a.lp = e->lp;
+    a.pb = e->pb;
+    int launches = 0;
+    lzb::MfTrace tr;
+    cudaError_t err = lzb::run_encode(a, e->scratch, e->num_sms, st, &launches, &tr);
+    add_launches(launches);
+    if (err != cudaSuccess) return fail(LZB_E_CUDA, "match finder: %s", cudaGetErrorString(err));
+    std::vector<uint32_t> idx, words;
+    try {
+        idx.resize((size_t)in_len + 1);
+        words.resize(tr.pair_words ? tr.pair_words : 1);
+    } catch (...) {
+        return fail(LZB_E_NOMEM, "out of host memory");
+    }
+    CUDA_TRY(cudaMemcpy(idx.data(), tr.idx, idx.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (tr.pair_words) CUDA_TRY(cudaMemcpy(words.data(), tr.pairs, (size_t)tr.pair_words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    uint64_t used = 0;
+    for (uint64_t p = 0; p < in_len; p++) {
+        const uint32_t off = idx[p + 1];
+        const uint32_t cnt = off == 0xFFFFFFFFu ? 0 : words[off];
+        counts[p] = cnt;
+        for (uint32_t k = 0; k < cnt; k++, used++) {
+            if (used < pairs_cap) {
+                const uint32_t w = words[off + 1 + k];
+                pairs[2 * used] = w >> 23;
+                pairs[2 * used + 1] = w & ((1u << 23) - 1);
+            }
+        }
+    }
+    if (pairs_used) *pairs_used = used;
+    return used <= pairs_cap ? LZB_OK : fail(LZB_E_CAPACITY, "pairs_cap %llu < %llu pairs", (unsigned long long)pairs_cap, (unsigned long long)used);
 }
 
 int lzb_enc_code(lzb_enc* e, const uint8_t* in, uint64_t in_len, uint8_t* out, uint64_t out_cap, uint64_t* out_len) {

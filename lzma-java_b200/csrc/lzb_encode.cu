@@ -92,7 +92,7 @@ size_t carve(uint8_t* base, uint32_t wb, uint32_t np, uint32_t hash_stride, uint
 
 }  // namespace
 
-cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cudaStream_t st, int* launches) {
+cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cudaStream_t st, int* launches, MfTrace* mf_only) {
     int nl = 0;
     if (launches) *launches = 0;
     if (a.n == 0) return cudaSuccess;
@@ -175,6 +175,18 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
             continue;
         }
 
+        if (mf_only) {  // trace tap: hand back block 0's lists instead of parsing
+            uint32_t used = 0;
+            e = cudaMemcpyAsync(&used, w.pair_used, sizeof used, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return e;
+            mf_only->idx = w.idx;
+            mf_only->pairs = w.pairs;
+            mf_only->pair_words = used;
+            if (launches) *launches = nl;
+            return cudaSuccess;
+        }
         pa.mf = w;
         pa.out = a.out;
         pa.out_off = a.out_off + done;

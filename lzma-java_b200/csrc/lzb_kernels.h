@@ -63,7 +63,16 @@ struct EncScratch {
 constexpr uint64_t kEncMaxBlockBytes = 1ull << 23;  // match pairs pack len << 23 | distance
 constexpr int kEncMaxWarps = 9;            // upper bound of parser streams resident per SM (shared memory decides, see parse_geometry)
 
-// Enqueue the whole encode pipeline for the batch on `st`.
-cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cudaStream_t st, int* launches);
+// where the match finder left the lists of the first block of a batch (trace tap)
+struct MfTrace {
+    const uint32_t* idx = nullptr;    // [len + 1], 1-based: offset into pairs or 0xFFFFFFFF
+    const uint32_t* pairs = nullptr;  // count, then count x (len << 23 | distance)
+    uint32_t pair_words = 0;          // words in use
+};
+
+// Enqueue the whole encode pipeline for the batch on `st`.  With `mf_only` the match finder
+// alone runs (one wave) and *mf_only describes the lists of block 0; the stream is synchronised.
+cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cudaStream_t st, int* launches,
+                       MfTrace* mf_only = nullptr);
 
 }  // namespace lzb

@@ -187,3 +187,40 @@ def test_encode_many_tiny_blocks_and_pair_overflow_retry(lzb, oracle, corpus, mo
     monkeypatch.setenv("LZB_PAIR_MUL", "1")
     text = [corpus.generate(60000, 1, 0, 27, k).tobytes() for k in range(3)]
     _check(lzb, oracle, BASE, text)
+
+
+@pytest.mark.parametrize("kw", [{}, {"fb": 64}, {"fb": 273, "dict_size": 1 << 23}, {"mf": 0}, {"dict_size": 4096}, {"dict_size": 1}])
+def test_match_finder_lists_equal_the_instrumented_trace(lzb, oracle, corpus, kw):
+    """North-star subsystem 1: the per-position (length, distance) lists of the parallel bt4/bt2
+    match finder are identical to the oracle's trace of BinTree.fillMatches0 / Skip for EVERY
+    position (BinTree.java:139-356), not just where the parser happened to look."""
+    p = dict(BASE)
+    p.update(kw)
+    for cls in range(4):
+        data = corpus.generate(30000 + 1111 * cls, 1, cls, 28, cls).tobytes()
+        _, tr = oracle.encode(data, oracle.props(**p), trace=True)
+        ref_counts = np.diff(tr["mf_off"].astype(np.int64))
+        enc = _encoder(lzb, p)
+        counts, pairs = enc.trace_matches(data)
+        enc.close()
+        assert np.array_equal(counts.astype(np.int64), ref_counts), (kw, cls)
+        # the parser truncates a list in place near the end of a chunk (Encoder.java:737-743), which the
+        # oracle's tap records before; compare the untouched (length, distance) pairs
+        assert np.array_equal(pairs.astype(np.int64), tr["mf_pairs"].astype(np.int64)), (kw, cls)
+
+
+def test_reference_learning_test_inputs(lzb, oracle):
+    """The four inputs of LZMA/EncoderLearningTest.java:35-38 with the class defaults (Encoder.java:26-27,151-158):
+    the reference prints a trace and asserts nothing; here GPU == oracle and the round trip holds."""
+    inputs = [bytes([99, 100, 98, 100, 100, 100, 100, 100, 100, 100, 100]),
+              bytes([100, 101, 102, 103, 104, 105, 101, 102, 101, 102]),
+              bytes([100, 101, 102, 103, 101, 104, 101, 101, 101]),
+              bytes([100, 100, 100, 101, 100, 100, 100, 101, 100, 100, 100, 101])]
+    enc = lzb.Encoder()  # class defaults: dict 1 << 22, fb 32, lc3 lp0 pb2, bt4
+    p = oracle.props()
+    for data in inputs:
+        payload = enc.code_bytes(data)
+        assert payload == oracle.encode(data, p)
+        ok, back = oracle.decode(oracle.props_bytes(p), payload, len(data))
+        assert ok == 1 and back == data
+    enc.close()
