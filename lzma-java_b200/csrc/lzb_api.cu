@@ -65,26 +65,42 @@ struct lzb_dec {
     DevBuf lit;      // spilled literal models
     DevBuf d_in, d_out, d_meta;
     PinBuf h_meta;
-    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-buffer batches overlap transfers with the kernel
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-buffer batches overlap transfers with the kernels
+    cudaStream_t kstream[4] = {nullptr, nullptr, nullptr, nullptr};  // ... whose chunks share the SMs
 };
 
 namespace {
 
-// literal-model size (16-bit slots) a stream needs outside shared memory, 0 if its model fits
-// (the host-side twin of lzb_decode_scan_headers)
-uint32_t spill_slots(const uint8_t* stream, uint64_t len) {
-    if (len < LZB_HEADER_SIZE) return 0;
+// the host-side twin of lzb_decode_scan_headers: running max of lc + lp + 1 and pb + 1 over well-formed headers
+void header_scan(const uint8_t* stream, uint64_t len, uint32_t* max_lclp1, uint32_t* max_pb1) {
+    if (len < LZB_HEADER_SIZE) return;
     const uint32_t v = stream[0];
-    const int lc = v % 9, rem = v / 9, lp = rem % 5, pb = rem / 5;
-    if (pb > 4) return 0;
-    const lzb::ModelLayout L = lzb::make_layout(lc, lp, pb);
-    return (size_t)(L.n_fixed + L.n_literal) * 2 > lzb::kDecSliceBytes ? (uint32_t)L.n_literal : 0;
+    const uint32_t lc = v % 9, rem = v / 9, lp = rem % 5, pb = rem / 5;
+    if (pb > 4) return;
+    if (lc + lp + 1 > *max_lclp1) *max_lclp1 = lc + lp + 1;
+    if (pb + 1 > *max_pb1) *max_pb1 = pb + 1;
+}
+
+// Where the models of a launch live (lzb_kernels.h, DecMode).  `resident` = streams that will be
+// in flight together: the hybrid mode trades a slower literal-after-match for twice the
+// streams per SM, which only pays when the all-shared mode could not hold them at once.
+int pick_dec_mode(uint32_t max_lclp1, uint32_t max_pb1, uint64_t resident, int num_sms) {
+    if (max_lclp1 > 4) return lzb::kDecGlobal;
+    if (max_lclp1 == 0) return lzb::kDecSmem;  // no well-formed header: every stream returns 0 at once
+    const lzb::ModelLayout L = lzb::make_layout((int)max_lclp1 - 1, 0, (int)max_pb1 - 1);
+    if ((size_t)(L.n_fixed + L.n_literal) * 2 > lzb::kDecSliceBytes) return lzb::kDecHybrid;  // lc + lp = 3 with pb = 4
+    if (const char* e = getenv("LZB_DEC_MODE")) {  // test hook: 0 = all shared, 1 = hybrid
+        if (e[0] == '0') return lzb::kDecSmem;
+        if (e[0] == '1') return lzb::kDecHybrid;
+    }
+    return resident > (uint64_t)num_sms * lzb::kDecMaxWarps ? lzb::kDecHybrid : lzb::kDecSmem;
 }
 
 // enqueue the decode kernel for n streams (no header scan, no synchronisation)
 int dec_enqueue(lzb_dec* d, const uint8_t* d_in, const uint64_t* d_in_off, const uint64_t* d_in_len, uint32_t n,
                 uint8_t* d_out, const uint64_t* d_out_off, const uint64_t* d_out_cap, uint64_t* d_out_len,
-                int32_t* d_status, uint32_t max_spill, uint32_t* ticket, cudaStream_t st) {
+                int32_t* d_status, uint32_t max_lclp1, int mode, uint32_t* ticket, cudaStream_t st, uint32_t region = 0,
+                uint32_t n_regions = 1) {
     lzb::DecodeArgs a;
     a.in = d_in;
     a.in_off = d_in_off;
@@ -98,13 +114,14 @@ int dec_enqueue(lzb_dec* d, const uint8_t* d_in, const uint64_t* d_in_off, const
     a.ticket = ticket;
     a.lit_scratch = nullptr;
     a.lit_stride = 0;
-    if (max_spill) {
-        a.lit_stride = max_spill;
-        const size_t slots = (size_t)d->num_sms * lzb::kDecMaxWarps;
-        CUDA_TRY(d->lit.reserve(slots * a.lit_stride * sizeof(uint16_t)));
-        a.lit_scratch = (uint16_t*)d->lit.p;
+    if (mode != lzb::kDecSmem && max_lclp1) {
+        a.lit_stride = (size_t)(mode == lzb::kDecHybrid ? 0x200 : 0x300) << (max_lclp1 - 1);
+        const size_t slots = (size_t)d->num_sms * lzb::dec_mode_warps(mode);
+        // launches that may run side by side (one per `kstream`) get a region each
+        CUDA_TRY(d->lit.reserve(n_regions * slots * a.lit_stride * sizeof(uint16_t)));
+        a.lit_scratch = (uint16_t*)d->lit.p + region * slots * a.lit_stride;
     }
-    CUDA_TRY(lzb::launch_decode(a, max_spill == 0, d->num_sms, st, nullptr, nullptr));
+    CUDA_TRY(lzb::launch_decode(a, mode, d->num_sms, st, nullptr, nullptr));
     add_launches(1);
     return LZB_OK;
 }
@@ -162,6 +179,8 @@ void lzb_dec_destroy(lzb_dec* d) {
     if (d->stream) cudaStreamDestroy(d->stream);
     if (d->copy_in) cudaStreamDestroy(d->copy_in);
     if (d->copy_out) cudaStreamDestroy(d->copy_out);
+    for (cudaStream_t k : d->kstream)
+        if (k) cudaStreamDestroy(k);
     delete d;
 }
 
@@ -192,14 +211,15 @@ int lzb_dec_code_batch_device(lzb_dec* d, const uint8_t* d_in, const uint64_t* d
     CUDA_TRY(cudaMemsetAsync(d->ctrl.p, 0, 64, st));
     uint32_t* ctrl = (uint32_t*)d->ctrl.p;
 
-    // which streams need their literal model outside shared memory?
+    // the largest lc + lp among the headers decides where the literal tables can live
     CUDA_TRY(lzb::launch_decode_scan(d_in, d_in_off, d_in_len, n, ctrl + 1, st));
     add_launches(1);
-    uint32_t max_spill = 0;
-    CUDA_TRY(cudaMemcpyAsync(&max_spill, ctrl + 1, sizeof max_spill, cudaMemcpyDeviceToHost, st));
+    uint32_t scan[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(scan, ctrl + 1, sizeof scan, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
 
-    return dec_enqueue(d, d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_cap, d_out_len, d_status, max_spill, ctrl, st);
+    return dec_enqueue(d, d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_cap, d_out_len, d_status, scan[0],
+                       pick_dec_mode(scan[0], scan[1], n, d->num_sms), ctrl, st);
 }
 
 int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len, uint32_t n,
@@ -225,24 +245,28 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
     CUDA_TRY(d->d_meta.reserve(meta_bytes));
     CUDA_TRY(d->h_meta.reserve(meta_bytes));
     uint64_t* hm = (uint64_t*)d->h_meta.p;
-    uint32_t max_spill = 0;
+    uint32_t max_lclp1 = 0, max_pb1 = 0;
     for (uint32_t i = 0; i < n; i++) {
         hm[i] = in_off[i] - si.lo;
         hm[n + i] = in_len[i];
         hm[2 * (size_t)n + i] = out_off[i] - so.lo;
         hm[3 * (size_t)n + i] = out_cap[i];
-        const uint32_t sp = spill_slots(in + in_off[i], in_len[i]);
-        if (sp > max_spill) max_spill = sp;
+        header_scan(in + in_off[i], in_len[i], &max_lclp1, &max_pb1);
     }
     uint64_t* dm = (uint64_t*)d->d_meta.p;
     uint8_t* d_in = (uint8_t*)d->d_in.p;
     uint8_t* d_out = (uint8_t*)d->d_out.p;
 
-    // One kernel launch decodes one "wave" (num_sms x 15 resident streams).  Launching wave by wave
-    // costs nothing (the waves would run back to back inside one launch anyway) and lets the
-    // input copy of wave k+1 and the output copy of wave k-1 overlap the kernel of wave k.
-    const uint32_t wave = (uint32_t)d->num_sms * lzb::kDecMaxWarps;
-    uint32_t n_chunks = (n + wave - 1) / wave;
+    // The batch is cut into chunks of about 7 streams per SM, each with its own input copy,
+    // kernel launch and output copy.  The kernels go round-robin over up to four streams so that
+    // chunks share the SMs (4 x 7 warps = the residency of one big launch) while the input of
+    // later chunks and the output of earlier ones are still on the PCIe bus.
+    const int mode = pick_dec_mode(max_lclp1, max_pb1, n, d->num_sms);
+    const uint32_t n_k = mode == lzb::kDecGlobal ? 1u : 4u;  // kDecGlobal: scratch can be GBs, one launch at a time
+    for (uint32_t k = 0; k < n_k; k++)
+        if (!d->kstream[k]) CUDA_TRY(cudaStreamCreateWithFlags(&d->kstream[k], cudaStreamNonBlocking));
+    const uint32_t per_chunk = (uint32_t)d->num_sms * 7;
+    uint32_t n_chunks = (n + per_chunk - 1) / per_chunk;
     if (n_chunks > 16) n_chunks = 16;
     std::vector<uint32_t> first(n_chunks + 1);
     std::vector<Span> cin(n_chunks), cout(n_chunks);
@@ -279,12 +303,16 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
             err = cudaMemcpyAsync(d_in + (cin[c].lo - si.lo), in + cin[c].lo, cin[c].hi - cin[c].lo, cudaMemcpyHostToDevice, d->copy_in);
         if (err != cudaSuccess) break;
         cudaEventRecord(ev_in[c], d->copy_in);
-        cudaStreamWaitEvent(st, ev_in[c], 0);
+        cudaStream_t ks = d->kstream[c % n_k];
+        cudaStreamWaitEvent(ks, ready, 0);
+        cudaStreamWaitEvent(ks, ev_in[c], 0);
         rc = dec_enqueue(d, d_in, dm + s0, dm + n + s0, cnt, d_out, dm + 2 * (size_t)n + s0, dm + 3 * (size_t)n + s0,
-                         dm + 4 * (size_t)n + s0, (int32_t*)(dm + 5 * (size_t)n) + s0, max_spill, (uint32_t*)d->ctrl.p + c, st);
+                         dm + 4 * (size_t)n + s0, (int32_t*)(dm + 5 * (size_t)n) + s0, max_lclp1, mode,
+                         (uint32_t*)d->ctrl.p + c, ks, c % n_k, n_k);
         if (rc != LZB_OK) break;
-        cudaEventRecord(ev_k[c], st);
+        cudaEventRecord(ev_k[c], ks);
         cudaStreamWaitEvent(d->copy_out, ev_k[c], 0);
+        cudaStreamWaitEvent(st, ev_k[c], 0);  // the out_len / status read-back below follows every kernel
         if (cout[c].hi > cout[c].lo)
             err = cudaMemcpyAsync(out + cout[c].lo, d_out + (cout[c].lo - so.lo), cout[c].hi - cout[c].lo, cudaMemcpyDeviceToHost,
                                   d->copy_out);
@@ -292,7 +320,12 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
     if (rc == LZB_OK && err == cudaSuccess)
         err = cudaMemcpyAsync(hm + 4 * (size_t)n, dm + 4 * (size_t)n, (size_t)n * (sizeof(uint64_t) + sizeof(int32_t)),
                               cudaMemcpyDeviceToHost, st);
-    const cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(d->copy_out), e3 = cudaStreamSynchronize(d->copy_in);
+    cudaError_t e1 = cudaStreamSynchronize(st);
+    const cudaError_t e2 = cudaStreamSynchronize(d->copy_out), e3 = cudaStreamSynchronize(d->copy_in);
+    for (uint32_t k = 0; k < n_k; k++) {
+        const cudaError_t ek = cudaStreamSynchronize(d->kstream[k]);
+        if (e1 == cudaSuccess) e1 = ek;
+    }
     cudaEventDestroy(ready);
     for (uint32_t c = 0; c < n_events; c++) {
         cudaEventDestroy(ev_in[c]);

@@ -54,12 +54,30 @@ struct RangeDec {
             fetch();
         }
     }
+    // RangeDecoder.java:33-37,58-62.  Only lane 0 runs the range decoder, so the branch
+    // cannot diverge: `bra.uni` tells ptxas, which then drops the BSSY/BSYNC pair it
+    // would otherwise wrap around every normalisation (2 of 20 instructions per bit).
     __device__ __forceinline__ void normalize() {
-        if (range < kTopValue) {
-            range <<= 8;
-            code = (code << 8) | nextb;
-            fetch();
-        }
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q, h;\n\t"
+            ".reg .u64 ad;\n\t"
+            "setp.gt.u32 q, %0, 0xFFFFFF;\n\t"
+            "@q bra.uni NORM_DONE;\n\t"
+            "shl.b32 %0, %0, 8;\n\t"
+            "shl.b32 %1, %1, 8;\n\t"
+            "or.b32 %1, %1, %2;\n\t"
+            "setp.lt.u32 h, %3, %4;\n\t"
+            "cvt.u64.u32 ad, %3;\n\t"
+            "add.u64 ad, ad, %5;\n\t"
+            "mov.u32 %2, 0xFFFFFFFF;\n\t"
+            "@h ld.global.nc.u8 %2, [ad];\n\t"
+            "add.u32 %3, %3, 1;\n\t"
+            "NORM_DONE:\n\t"
+            "}"
+            : "+r"(range), "+r"(code), "+r"(nextb), "+r"(ip)
+            : "r"(len), "l"(in)
+            : "memory");
     }
     // RangeDecoder.DecodeBit (:43-64) on a shared-memory probability, branch-free:
     //   bit 0: p += (2048 - p) >> 5      bit 1: p -= p >> 5
@@ -94,6 +112,40 @@ struct RangeDec {
         normalize();
         return b;
     }
+    // One level of a bit tree: decode the bit at shared address `a` and move to the child,
+    //   a' = sbase + 2 * (2 m + bit) = 2 a - sbase + 2 bit      (a = sbase + 2 m)
+    // with `nsb` = -sbase; the predicate feeds the address directly (no 0/1 materialised):
+    // 18 instructions per level against 20 for `m = (m << 1) + bit_s(...)`.
+    __device__ __forceinline__ void tree_step(uint32_t& a, uint32_t nsb) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred z;\n\t"
+            ".reg .u16 ph;\n\t"
+            ".reg .u32 p, t, bound, r1, k, a2;\n\t"
+            ".reg .s32 d;\n\t"
+            "ld.shared.u16 ph, [%2];\n\t"
+            "cvt.u32.u16 p, ph;\n\t"
+            "shr.u32 t, %0, 11;\n\t"
+            "mul.lo.u32 bound, t, p;\n\t"
+            "setp.lt.u32 z, %1, bound;\n\t"
+            "sub.u32 r1, %0, bound;\n\t"
+            "selp.u32 %0, bound, r1, z;\n\t"
+            "@!z sub.u32 %1, %1, bound;\n\t"
+            "selp.u32 k, 2017, 0, z;\n\t"
+            "sub.s32 d, p, k;\n\t"
+            "shr.s32 d, d, 5;\n\t"
+            "sub.u32 p, p, d;\n\t"
+            "cvt.u16.u32 ph, p;\n\t"
+            "st.shared.u16 [%2], ph;\n\t"
+            "add.u32 a2, %2, %2;\n\t"
+            "add.u32 %2, a2, %3;\n\t"
+            "@!z add.u32 %2, %2, 2;\n\t"
+            "}"
+            : "+r"(range), "+r"(code), "+r"(a)
+            : "r"(nsb)
+            : "memory");
+        normalize();
+    }
     // the same on a generic pointer (literal coders spilled to global memory)
     __device__ __forceinline__ uint32_t bit_g(uint16_t* prob) {
         const uint32_t p0 = *prob;
@@ -122,16 +174,18 @@ struct RangeDec {
     // BitTreeDecoder.Decode (BitTreeDecoder.java:19-25); `m2` walks the tree as a byte offset (2 * m)
     template <int NBITS>
     __device__ __forceinline__ uint32_t tree(uint32_t sbase) {
-        uint32_t m2 = 2;
+        uint32_t a = sbase + 2;
+        const uint32_t nsb = 0u - sbase;
 #pragma unroll
-        for (int i = 0; i < NBITS; i++) m2 = (m2 << 1) + (bit_s(sbase + m2) << 1);
-        return (m2 >> 1) - (1u << NBITS);
+        for (int i = 0; i < NBITS; i++) tree_step(a, nsb);
+        return ((a + nsb) >> 1) - (1u << NBITS);
     }
     __device__ __forceinline__ uint32_t tree_n(uint32_t sbase, int nbits) {
-        uint32_t m2 = 2;
+        uint32_t a = sbase + 2;
+        const uint32_t nsb = 0u - sbase;
 #pragma unroll 1
-        for (int i = 0; i < nbits; i++) m2 = (m2 << 1) + (bit_s(sbase + m2) << 1);
-        return (m2 >> 1) - (1u << nbits);
+        for (int i = 0; i < nbits; i++) tree_step(a, nsb);
+        return ((a + nsb) >> 1) - (1u << nbits);
     }
     // BitTreeDecoder.ReverseDecode (:27-37) / Decoder.ReverseDecode (Decoder.java:13-23)
     __device__ __forceinline__ uint32_t reverse(uint32_t sbase, int nbits) {
@@ -155,10 +209,11 @@ __device__ __forceinline__ uint32_t decode_len(RangeDec& rd, uint32_t slen, int 
 
 // LiteralDecoder.Decoder2.DecodeNormal (Decoder.java:70-77), unrolled
 __device__ __forceinline__ uint32_t decode_literal_s(RangeDec& rd, uint32_t sprobs) {
-    uint32_t m2 = 2;
+    uint32_t a = sprobs + 2;
+    const uint32_t nsb = 0u - sprobs;
 #pragma unroll
-    for (int i = 0; i < 8; i++) m2 = (m2 << 1) + (rd.bit_s(sprobs + m2) << 1);
-    return (m2 >> 1) & 0xFF;
+    for (int i = 0; i < 8; i++) rd.tree_step(a, nsb);
+    return ((a + nsb) >> 1) & 0xFF;
 }
 // DecodeWithMatchByte (Decoder.java:79-95): `offs` is 0x100 while the decoded bits still agree
 // with the match byte (probability index ((1 + matchBit) << 8) + symbol), 0 afterwards.
@@ -172,6 +227,23 @@ __device__ __forceinline__ uint32_t decode_literal_matched_s(RangeDec& rd, uint3
         symbol = (symbol << 1) | b;
         offs &= b ? mb : ~mb;
     } while (symbol < 0x100);
+    return symbol & 0xFF;
+}
+// kDecHybrid: the matched tables (indices 0x100..0x2FF of a coder) are `gprobs` in global memory,
+// 0x200 slots per coder; once a bit disagrees with the match byte the walk continues in the
+// coder's normal tree in shared memory (0x100 slots per coder at `sprobs`).
+__device__ __forceinline__ uint32_t decode_literal_matched_h(RangeDec& rd, uint32_t sprobs, uint16_t* gprobs, uint32_t match_byte) {
+    uint32_t symbol = 1;
+#pragma unroll 1
+    do {
+        match_byte <<= 1;
+        const uint32_t mb = match_byte & 0x100u;
+        const uint32_t b = rd.bit_g(gprobs + mb + symbol);
+        symbol = (symbol << 1) | b;
+        if ((mb >> 8) != b) break;
+    } while (symbol < 0x100);
+#pragma unroll 1
+    while (symbol < 0x100) symbol = (symbol << 1) | rd.bit_s(sprobs + 2 * symbol);
     return symbol & 0xFF;
 }
 // both forms on a generic pointer
@@ -190,7 +262,7 @@ __device__ __forceinline__ uint32_t decode_literal_g(RangeDec& rd, uint16_t* pro
 
 enum : int { EV_MATCH = 0, EV_DONE = 1, EV_DATA_ERROR = 2, EV_CAPACITY = 3 };
 
-template <bool LIT_SMEM>
+template <int MODE>
 __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, uint16_t* lit_global, int lane) {
     const uint64_t in_len = a.in_len[s];
     const uint8_t* in = a.in + a.in_off[s];
@@ -214,13 +286,17 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
         for (int i = 0; i < 8; i++) usize |= (uint64_t)in[5 + i] << (8 * i);
         // SetLcLpPb (:172-182) rejects pb > 4 (lc, lp are bounded by the
         // arithmetic); SetDictionarySize (:160-170) rejects a negative size.
+        const ModelLayout L = make_layout(lc, lp, pb);
+        // literal slots in shared / global memory for this mode
+        const int n_lit_s = MODE == kDecSmem ? L.n_literal : MODE == kDecHybrid ? 0x100 << (lc + lp) : 0;
+        const int n_lit_g = MODE == kDecSmem ? 0 : MODE == kDecHybrid ? 0x200 << (lc + lp) : L.n_literal;
         if (pb > 4 || (int32_t)dict < 0) {
             status = 0;
+        } else if ((size_t)(L.n_fixed + n_lit_s) * 2 > dec_mode_slice(MODE) || (MODE != kDecSmem && (size_t)n_lit_g > a.lit_stride)) {
+            status = LZB_KERNEL_E_UNSUPPORTED;  // the host picked a mode this stream's lc/lp/pb does not fit
         } else {
-            const ModelLayout L = make_layout(lc, lp, pb);
-            uint16_t* lit = LIT_SMEM ? model + L.literal : lit_global;
-            for (int i = lane; i < L.n_fixed; i += 32) model[i] = kProbInit;  // Decoder.Init :184-203
-            for (int i = lane; i < L.n_literal; i += 32) lit[i] = kProbInit;
+            for (int i = lane; i < L.n_fixed + n_lit_s; i += 32) model[i] = kProbInit;  // Decoder.Init :184-203
+            for (int i = lane; i < n_lit_g; i += 32) lit_global[i] = kProbInit;
             __syncwarp();
 
             const uint32_t dict_check = dict > 1 ? dict : 1;  // m_DictionarySizeCheck :166
@@ -233,6 +309,9 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
             int state = 0;
             uint32_t rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0;
             uint32_t prev_byte = 0, match_byte = 0;
+            uint32_t pend_b = 0;  // deferred tail of the last match copy (one byte per lane)
+            uint8_t* pend_dst = out;
+            bool pend_valid = false;
             if (lane == 0) rd.init(in + LZB_KERNEL_HEADER, (uint32_t)(in_len - LZB_KERNEL_HEADER));
 
             for (;;) {
@@ -244,12 +323,16 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
                     while (pos < limit) {  // Decoder.Code :219
                         const uint32_t pos_state = pos & pos_mask;
                         if (rd.bit_s(sm + 2 * (L.is_match + (state << pb) + pos_state)) == 0) {
-                            const uint32_t coder = 0x300u * (((pos & lp_mask) << lc) + (prev_byte >> (8 - lc)));
-                            if (LIT_SMEM) {
-                                const uint32_t sprobs = sm + 2 * (L.literal + coder);
+                            const uint32_t ctx = ((pos & lp_mask) << lc) + (prev_byte >> (8 - lc));
+                            if (MODE == kDecSmem) {
+                                const uint32_t sprobs = sm + 2 * (L.literal + 0x300u * ctx);
                                 prev_byte = state >= 7 ? decode_literal_matched_s(rd, sprobs, match_byte) : decode_literal_s(rd, sprobs);
+                            } else if (MODE == kDecHybrid) {
+                                const uint32_t sprobs = sm + 2 * (L.literal + 0x100u * ctx);
+                                prev_byte = state >= 7 ? decode_literal_matched_h(rd, sprobs, lit_global + 0x200u * ctx, match_byte)
+                                                       : decode_literal_s(rd, sprobs);
                             } else {
-                                prev_byte = decode_literal_g(rd, lit_global + coder, state >= 7, match_byte);
+                                prev_byte = decode_literal_g(rd, lit_global + 0x300u * ctx, state >= 7, match_byte);
                             }
                             if (pos >= cap) { ev = EV_CAPACITY; break; }
                             out[pos] = (uint8_t)prev_byte;
@@ -318,6 +401,9 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
                     evlen = (uint32_t)ev | (len << 2);
                 }
                 evlen = __shfl_sync(kFull, evlen, 0);
+                // the tail of the previous match is still in registers: store it now that its loads
+                // have landed (lane 0 decoded a whole symbol under their L2 latency)
+                if (pend_valid) *pend_dst = (uint8_t)pend_b;
                 const int ev = (int)(evlen & 3);
                 if (ev != EV_MATCH) {
                     status = ev == EV_DONE ? 1 : (ev == EV_DATA_ERROR ? 0 : LZB_KERNEL_E_CAPACITY);
@@ -330,26 +416,21 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
                 __syncwarp();  // order earlier stores (lane 0's literals, other lanes' copies) before these loads
                 const uint8_t* src = out + pos - d;
                 uint8_t* dst = out + pos;
-                uint32_t last = 0, next = 0;
-                // index k = len is loaded but not stored: it is the byte GetByte(rep0) will
-                // return for a matched literal that follows (Decoder.java:227).
-                if (d > len) {
-                    for (uint32_t k = lane; k <= len; k += 32) {
-                        const uint32_t b = src[k];
-                        if (k < len) dst[k] = (uint8_t)b;
-                        if (k == len - 1) last = b;
-                        if (k == len) next = b;
-                    }
-                } else {
-                    for (uint32_t k = lane; k <= len; k += 32) {
-                        const uint32_t b = src[k % d];
-                        if (k < len) dst[k] = (uint8_t)b;
-                        if (k == len - 1) last = b;
-                        if (k == len) next = b;
-                    }
+                const bool wraps = d <= len;
+                // lane 0 also fetches the two bytes a literal after this match would need, GetByte(0)
+                // (:294) and GetByte(rep0) (:227); nothing waits for them unless that literal comes.
+                if (lane == 0) {
+                    prev_byte = src[wraps ? (len - 1) % d : len - 1];
+                    match_byte = src[wraps ? len % d : len];
                 }
-                prev_byte = __shfl_sync(kFull, last, (len - 1) & 31);  // GetByte(0) :294
-                match_byte = __shfl_sync(kFull, next, len & 31);
+                // all 32-byte chunks but the last are stored at once; the last stays pending
+                uint32_t k = lane;
+                for (uint32_t chunks = (len - 1) >> 5; chunks != 0; chunks--, k += 32) dst[k] = src[wraps ? k % d : k];
+                pend_valid = k < len;
+                if (pend_valid) {
+                    pend_b = src[wraps ? k % d : k];
+                    pend_dst = dst + k;
+                }
                 pos += len;
             }
         }
@@ -360,55 +441,56 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
     }
 }
 
-template <bool LIT_SMEM>
-__global__ void __launch_bounds__(kDecMaxWarps * 32, 1) lzb_decode_kernel(DecodeArgs a) {
+template <int MODE>
+__global__ void __launch_bounds__(dec_mode_warps(MODE) * 32, 1) lzb_decode_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) uint16_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint16_t* model = smem + (size_t)warp * (kDecSliceBytes / 2);
-    uint16_t* lit_global = LIT_SMEM ? nullptr
-                                    : a.lit_scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * a.lit_stride;
+    uint16_t* model = smem + (size_t)warp * (dec_mode_slice(MODE) / 2);
+    uint16_t* lit_global = MODE == kDecSmem ? nullptr
+                                            : a.lit_scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * a.lit_stride;
     for (;;) {
         uint32_t s = 0;
         if (lane == 0) s = atomicAdd(a.ticket, 1u);
         s = __shfl_sync(kFull, s, 0);
         if (s >= a.n) break;
-        decode_stream<LIT_SMEM>(a, s, model, lit_global, lane);
+        decode_stream<MODE>(a, s, model, lit_global, lane);
     }
 }
 
-// Header pre-pass: the largest literal model (in 16-bit slots) among streams
-// whose model does not fit a warp's shared-memory slice; 0 if all fit.
+// Header pre-pass: max over well-formed streams of lc + lp + 1 (0 if there is none) and of pb + 1.
 __global__ void lzb_decode_scan_headers(const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len, uint32_t n,
-                                        uint32_t* max_spill) {
+                                        uint32_t* max_lclp1) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (in_len[i] < LZB_KERNEL_HEADER) return;
     const uint32_t v = in[in_off[i]];
     const int lc = v % 9, rem = v / 9, lp = rem % 5, pb = rem / 5;
     if (pb > 4) return;
-    const ModelLayout L = make_layout(lc, lp, pb);
-    if ((size_t)(L.n_fixed + L.n_literal) * 2 > kDecSliceBytes) atomicMax(max_spill, (uint32_t)L.n_literal);
+    atomicMax(max_lclp1, (uint32_t)(lc + lp + 1));
+    atomicMax(max_lclp1 + 1, (uint32_t)(pb + 1));
 }
 
 cudaError_t launch_decode_scan(const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len, uint32_t n,
-                               uint32_t* d_max_spill, cudaStream_t st) {
+                               uint32_t* d_max_lclp1, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    lzb_decode_scan_headers<<<(n + 255) / 256, 256, 0, st>>>(in, in_off, in_len, n, d_max_spill);
+    lzb_decode_scan_headers<<<(n + 255) / 256, 256, 0, st>>>(in, in_off, in_len, n, d_max_lclp1);
     return cudaGetLastError();
 }
 
-cudaError_t launch_decode(const DecodeArgs& a, bool lit_in_smem, int num_sms, cudaStream_t st, int* grid_out, int* warps_out) {
+cudaError_t launch_decode(const DecodeArgs& a, int mode, int num_sms, cudaStream_t st, int* grid_out, int* warps_out) {
     if (a.n == 0) return cudaSuccess;
+    const int max_warps = dec_mode_warps(mode);
+    const size_t slice = dec_mode_slice(mode);
     int warps = (int)((a.n + (uint32_t)num_sms - 1) / (uint32_t)num_sms);
-    if (warps > kDecMaxWarps) warps = kDecMaxWarps;
+    if (warps > max_warps) warps = max_warps;
     if (warps < 1) warps = 1;
     int grid = (int)((a.n + (uint32_t)warps - 1) / (uint32_t)warps);
     if (grid > num_sms) grid = num_sms;
-    const size_t smem = (size_t)warps * kDecSliceBytes;
-    auto kern = lit_in_smem ? lzb_decode_kernel<true> : lzb_decode_kernel<false>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kDecMaxWarps * kDecSliceBytes));
+    auto kern = mode == kDecSmem ? lzb_decode_kernel<kDecSmem>
+                                 : mode == kDecHybrid ? lzb_decode_kernel<kDecHybrid> : lzb_decode_kernel<kDecGlobal>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(max_warps * slice));
     if (err != cudaSuccess) return err;
-    kern<<<grid, warps * 32, smem, st>>>(a);
+    kern<<<grid, warps * 32, (size_t)warps * slice, st>>>(a);
     if (grid_out) *grid_out = grid;
     if (warps_out) *warps_out = warps;
     return cudaGetLastError();

@@ -13,8 +13,21 @@
 namespace lzb {
 
 // ---- decoder ---------------------------------------------------------------
-constexpr int kDecMaxWarps = 15;          // streams resident per SM
+// Where a stream's probability model lives.  Streams per SM are bounded by shared memory, and
+// two thirds of an lc=3 model are the matched-literal tables (Decoder.java:79-95) that only a
+// literal right after a match touches: the hybrid mode keeps them in global memory (L2) and
+// almost doubles the resident streams.  It pays when there are more streams than kDecSmem slots.
+enum DecMode : int {
+    kDecSmem = 0,    // whole model in shared memory (lc + lp <= 3)
+    kDecHybrid = 1,  // matched-literal tables in global memory (lc + lp <= 3)
+    kDecGlobal = 2,  // all literal tables in global memory (any lc, lp)
+};
+constexpr int kDecMaxWarps = 15;          // streams resident per SM, kDecSmem / kDecGlobal
 constexpr size_t kDecSliceBytes = 15488;  // 15 * 15488 = 232 320 B <= 227 KB per CTA
+constexpr int kDecHybridWarps = 28;       // 28 warps * 72 registers fill the register file
+constexpr size_t kDecHybridSlice = 7808;  // fixed part (pb = 4: 3696 B) + 8 normal literal trees (4096 B)
+__host__ __device__ constexpr int dec_mode_warps(int mode) { return mode == kDecHybrid ? kDecHybridWarps : kDecMaxWarps; }
+__host__ __device__ constexpr size_t dec_mode_slice(int mode) { return mode == kDecHybrid ? kDecHybridSlice : kDecSliceBytes; }
 
 struct DecodeArgs {
     const uint8_t* in;
@@ -27,14 +40,14 @@ struct DecodeArgs {
     int32_t* status;
     uint32_t n;
     uint32_t* ticket;        // zeroed before launch
-    uint16_t* lit_scratch;   // literal models that do not fit shared memory
-    size_t lit_stride;       // in 16-bit slots, per warp
+    uint16_t* lit_scratch;   // literal tables kept in global memory (kDecHybrid, kDecGlobal)
+    size_t lit_stride;       // in 16-bit slots, per resident stream
 };
 
+// header pre-pass over well-formed streams: d_max_lclp1[0] = max(lc + lp + 1) (0 if there is none), [1] = max(pb + 1)
 cudaError_t launch_decode_scan(const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len, uint32_t n,
-                               uint32_t* d_max_spill, cudaStream_t st);
-cudaError_t launch_decode(const DecodeArgs& a, bool lit_in_smem, int num_sms, cudaStream_t st, int* grid_out,
-                          int* warps_out);
+                               uint32_t* d_max_lclp1, cudaStream_t st);
+cudaError_t launch_decode(const DecodeArgs& a, int mode, int num_sms, cudaStream_t st, int* grid_out, int* warps_out);
 
 // ---- encoder ---------------------------------------------------------------
 struct EncodeArgs {

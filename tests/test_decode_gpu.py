@@ -3,11 +3,26 @@ streams produced by the CPU oracle (bit-identical to the reference encoder)
 and by liblzma must decode to the original bytes and agree with the oracle's
 decoder on return value and length, including corrupt and truncated input."""
 import lzma
+import os
 
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=["auto", "shared", "hybrid"])
+def dec_mode(request):
+    """Every test runs with the library's own choice of where the probability models live, with
+    all of them forced into shared memory, and with the matched-literal tables forced into
+    global memory (the mode big batches use; lzb_kernels.h DecMode)."""
+    old = os.environ.pop("LZB_DEC_MODE", None)
+    if request.param != "auto":
+        os.environ["LZB_DEC_MODE"] = "0" if request.param == "shared" else "1"
+    yield request.param
+    os.environ.pop("LZB_DEC_MODE", None)
+    if old is not None:
+        os.environ["LZB_DEC_MODE"] = old
 
 BASE = dict(dict_size=1 << 20, lc=3, lp=0, pb=2, fb=32, mf=1, eos=False)
 
@@ -141,8 +156,9 @@ def test_decoder_class_mirrors_reference(lzb, oracle, corpus):
 
 
 def test_decode_many_streams(lzb, oracle, corpus):
-    """More streams than resident warp slots (148 SMs x 15): exercises the ticket queue."""
-    n = 3000
+    """More streams than resident warp slots (148 SMs x 15, x 28 in hybrid mode): exercises the
+    ticket queue, and the chunked host pipeline with kernels of several chunks sharing the SMs."""
+    n = 5000
     data = corpus.generate(4096, n, corpus.MIXED, 11)
     off = np.arange(n, dtype=np.uint64) * 4096
     ln = np.full(n, 4096, dtype=np.uint64)
