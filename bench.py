@@ -40,7 +40,7 @@ if ROOT not in sys.path:
 DEC = dict(size=256 << 10, dict_size=1 << 20, fb=32, cls=0, config_id=2)   # configs[1]
 ENC = dict(size=1 << 20, dict_size=1 << 20, fb=64, cls=4, config_id=3)     # configs[2]
 METRIC = "LZMA batch decode, uncompressed input MB/s (bit-exact vs reference)"
-NCU_DRAM_BYTES_PER_LAUNCH = 5.065539e9 + 1.064341e9  # profiles/r01_decode_kernel_ncu.txt, 4096 x 256 KiB text streams
+NCU_DRAM_BYTES_PER_LAUNCH = 8.123094e9 + 1.182275e9  # profiles/r01_decode_hybrid_ncu.txt, 4096 x 256 KiB text streams
 
 
 def hbm_peak():
@@ -312,8 +312,8 @@ def run_b200(args, rank, world, local_rank):
             "gpu_launches": int(timed_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == 4096 else None,
-                         "traffic_source": "profiles/r01_decode_kernel_ncu.txt (dram__bytes_read+write, one ncu --set full capture of this launch shape)",
-                         "peak_source": peak_src, "kernel": "lzb_decode_kernel<true>",
+                         "traffic_source": "profiles/r01_decode_hybrid_ncu.txt (dram__bytes_read+write, one ncu --set full capture of this launch shape)",
+                         "peak_source": peak_src, "kernel": "lzb_decode_kernel<kDecHybrid>",
                          "algorithmic_bytes_per_launch": n * size + total_c, "kernel_ms": kernel_ms,
                          "note": "serial range-decoder chains: issue/latency bound, not HBM bound (profiles/)"},
             "clocks": clk.summary(), "compressed_ratio": total_c / (n * size),

@@ -80,8 +80,8 @@ struct RangeDec {
             : "memory");
     }
     // RangeDecoder.DecodeBit (:43-64) on a shared-memory probability, branch-free:
-    //   bit 0: p += (2048 - p) >> 5      bit 1: p -= p >> 5
-    // are both  p -= (p - k) >> 5 (arithmetic shift) with k = 2017 (= 2048 - 31) resp. 0.
+    //   bit 0: p += (2048 - p) >> 5 = (31 p + 2048) >> 5      bit 1: p -= p >> 5 = (31 p + 31) >> 5
+    // (p + floor(x / 32) = floor((32 p + x) / 32), and p - floor(p / 32) = ceil(31 p / 32)).
     __device__ __forceinline__ uint32_t bit_s(uint32_t saddr) {
         uint32_t b;
         asm volatile(
@@ -89,7 +89,6 @@ struct RangeDec {
             ".reg .pred z;\n\t"
             ".reg .u16 ph;\n\t"
             ".reg .u32 p, t, bound, r1, k;\n\t"
-            ".reg .s32 d;\n\t"
             "ld.shared.u16 ph, [%3];\n\t"
             "cvt.u32.u16 p, ph;\n\t"
             "shr.u32 t, %0, 11;\n\t"
@@ -98,10 +97,9 @@ struct RangeDec {
             "sub.u32 r1, %0, bound;\n\t"
             "selp.u32 %0, bound, r1, z;\n\t"
             "@!z sub.u32 %1, %1, bound;\n\t"
-            "selp.u32 k, 2017, 0, z;\n\t"
-            "sub.s32 d, p, k;\n\t"
-            "shr.s32 d, d, 5;\n\t"
-            "sub.u32 p, p, d;\n\t"
+            "selp.u32 k, 2048, 31, z;\n\t"
+            "mad.lo.u32 p, p, 31, k;\n\t"
+            "shr.u32 p, p, 5;\n\t"
             "cvt.u16.u32 ph, p;\n\t"
             "st.shared.u16 [%3], ph;\n\t"
             "selp.u32 %2, 0, 1, z;\n\t"
@@ -122,7 +120,6 @@ struct RangeDec {
             ".reg .pred z;\n\t"
             ".reg .u16 ph;\n\t"
             ".reg .u32 p, t, bound, r1, k, a2;\n\t"
-            ".reg .s32 d;\n\t"
             "ld.shared.u16 ph, [%2];\n\t"
             "cvt.u32.u16 p, ph;\n\t"
             "shr.u32 t, %0, 11;\n\t"
@@ -131,10 +128,9 @@ struct RangeDec {
             "sub.u32 r1, %0, bound;\n\t"
             "selp.u32 %0, bound, r1, z;\n\t"
             "@!z sub.u32 %1, %1, bound;\n\t"
-            "selp.u32 k, 2017, 0, z;\n\t"
-            "sub.s32 d, p, k;\n\t"
-            "shr.s32 d, d, 5;\n\t"
-            "sub.u32 p, p, d;\n\t"
+            "selp.u32 k, 2048, 31, z;\n\t"
+            "mad.lo.u32 p, p, 31, k;\n\t"
+            "shr.u32 p, p, 5;\n\t"
             "cvt.u16.u32 ph, p;\n\t"
             "st.shared.u16 [%2], ph;\n\t"
             "add.u32 a2, %2, %2;\n\t"
@@ -448,12 +444,13 @@ __global__ void __launch_bounds__(dec_mode_warps(MODE) * 32, 1) lzb_decode_kerne
     uint16_t* model = smem + (size_t)warp * (dec_mode_slice(MODE) / 2);
     uint16_t* lit_global = MODE == kDecSmem ? nullptr
                                             : a.lit_scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * a.lit_stride;
-    for (;;) {
-        uint32_t s = 0;
-        if (lane == 0) s = atomicAdd(a.ticket, 1u);
-        s = __shfl_sync(kFull, s, 0);
-        if (s >= a.n) break;
+    // first stream by position (warp-major, so a small batch spreads over all SMs), then by ticket
+    const uint32_t slots = gridDim.x * (blockDim.x >> 5);
+    uint32_t s = (uint32_t)warp * gridDim.x + blockIdx.x;
+    while (s < a.n) {
         decode_stream<MODE>(a, s, model, lit_global, lane);
+        if (lane == 0) s = slots + atomicAdd(a.ticket, 1u);
+        s = __shfl_sync(kFull, s, 0);
     }
 }
 
@@ -484,8 +481,9 @@ cudaError_t launch_decode(const DecodeArgs& a, int mode, int num_sms, cudaStream
     int warps = (int)((a.n + (uint32_t)num_sms - 1) / (uint32_t)num_sms);
     if (warps > max_warps) warps = max_warps;
     if (warps < 1) warps = 1;
-    int grid = (int)((a.n + (uint32_t)warps - 1) / (uint32_t)warps);
-    if (grid > num_sms) grid = num_sms;
+    // streams are handed out by ticket, so spread the warps over every SM (4096 streams: 148 CTAs
+    // of 28 warps with 48 idle warps, not 147 full CTAs and an idle SM)
+    const int grid = a.n < (uint32_t)num_sms ? (int)a.n : num_sms;
     auto kern = mode == kDecSmem ? lzb_decode_kernel<kDecSmem>
                                  : mode == kDecHybrid ? lzb_decode_kernel<kDecHybrid> : lzb_decode_kernel<kDecGlobal>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(max_warps * slice));
