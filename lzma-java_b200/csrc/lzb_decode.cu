@@ -5,19 +5,21 @@
 // (RangeCoder/BitTreeDecoder.java:19-37), LenDecoder / LiteralDecoder
 // (Decoder.java:25-127) and OutWindow.CopyBlock (LZ/OutWindow.java:53-67) of
 // rfalke/lzma-java.  Design (DESIGN.md section "decoder"):
-//   * one persistent CTA per SM, 15 warps, each warp owns one stream at a
-//     time and pulls the next one from a global ticket counter;
-//   * the stream's whole probability model (7 320 16-bit slots at lc3 lp0
-//     pb2) lives in the warp's private 15 488-byte slice of shared memory;
+//   * one persistent CTA per SM; each warp owns one stream at a time (the
+//     first by position, the following ones from a global ticket counter);
+//   * the stream's probability model lives in the warp's private slice of
+//     shared memory -- all of it (kDecSmem, 15 streams per SM), or all but the
+//     matched-literal tables, which then sit in global memory (kDecHybrid,
+//     28 streams per SM), or all but the literal coders (kDecGlobal, lc+lp > 3);
+//     see DecMode in lzb_kernels.h.  Residency is what the throughput hangs on;
 //   * lane 0 runs the serial range-decoder chain with range/code and a
-//     one-byte input lookahead in registers;
+//     one-byte input lookahead in registers; the bit decode is PTX;
 //   * matches are copied by all 32 lanes: out[pos+k] = out[pos-d+(k mod d)],
 //     which is order-free even when the match overlaps itself; the output
 //     buffer doubles as the dictionary window (a distance never exceeds the
 //     position, and the reference's rep0 >= dictionary check is kept);
-//   * the lane that loads index k = len also supplies the next match byte,
-//     the lane of k = len-1 the new previous byte, so lane 0 never re-reads
-//     global memory after a match.
+//   * nothing waits for a copy: its last 32 bytes stay in registers until the
+//     next copy, and lane 0 prefetches the two bytes a following literal needs.
 #include "lzb_common.cuh"
 #include "lzb_kernels.h"
 
@@ -25,11 +27,11 @@ namespace lzb {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
-// Range decoder state of one stream, in lane 0's registers.  The kernel is
-// issue-bound (profiles/: 63-75 % of issue slots busy with 15 streams per SM), so
-// the one thing that matters is the instruction count of a bit decode.  `bit_s`
-// is written in PTX against a shared-memory byte address: 13 instructions
-// (LDS, SHF, IMAD, ISETP, IADD, SEL, @IADD, SEL, IADD, SHF, IADD, STS, SEL).
+// Range decoder state of one stream, in lane 0's registers.  With 28 streams per
+// SM the kernel is issue-bound (profiles/r01_decode_hybrid_ncu.txt: 85 % of issue
+// slots busy), so what matters is the instruction count of a bit decode.  `bit_s`
+// is written in PTX against a shared-memory byte address: 12 instructions
+// (LDS, SHF, IMAD, ISETP, IADD, SEL, @IADD, SEL, IMAD, SHF, STS, SEL).
 struct RangeDec {
     uint32_t range, code, nextb, ip, len;
     const uint8_t* in;
