@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "lzb_common.cuh"
@@ -64,7 +65,7 @@ struct lzb_dec {
     DevBuf ctrl;     // [0] ticket, [1] max spill
     DevBuf lit;      // spilled literal models
     DevBuf d_in, d_out, d_meta;
-    PinBuf h_meta;
+    PinBuf h_meta, h_progress;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-buffer batches overlap transfers with the kernels
     cudaStream_t kstream[4] = {nullptr, nullptr, nullptr, nullptr};  // ... whose chunks share the SMs
 };
@@ -100,7 +101,7 @@ int pick_dec_mode(uint32_t max_lclp1, uint32_t max_pb1, uint64_t resident, int n
 int dec_enqueue(lzb_dec* d, const uint8_t* d_in, const uint64_t* d_in_off, const uint64_t* d_in_len, uint32_t n,
                 uint8_t* d_out, const uint64_t* d_out_off, const uint64_t* d_out_cap, uint64_t* d_out_len,
                 int32_t* d_status, uint32_t max_lclp1, int mode, uint32_t* ticket, cudaStream_t st, uint32_t region = 0,
-                uint32_t n_regions = 1) {
+                uint32_t n_regions = 1, uint32_t* progress = nullptr, uint32_t marks = 0, uint32_t mark_step = 0) {
     lzb::DecodeArgs a;
     a.in = d_in;
     a.in_off = d_in_off;
@@ -114,6 +115,9 @@ int dec_enqueue(lzb_dec* d, const uint8_t* d_in, const uint64_t* d_in_off, const
     a.ticket = ticket;
     a.lit_scratch = nullptr;
     a.lit_stride = 0;
+    a.progress = progress;
+    a.marks = marks;
+    a.mark_step = mark_step;
     if (mode != lzb::kDecSmem && max_lclp1) {
         a.lit_stride = (size_t)(mode == lzb::kDecHybrid ? 0x200 : 0x300) << (max_lclp1 - 1);
         const size_t slots = (size_t)d->num_sms * lzb::dec_mode_warps(mode);
@@ -176,6 +180,7 @@ void lzb_dec_destroy(lzb_dec* d) {
     d->d_out.release();
     d->d_meta.release();
     d->h_meta.release();
+    d->h_progress.release();
     if (d->stream) cudaStreamDestroy(d->stream);
     if (d->copy_in) cudaStreamDestroy(d->copy_in);
     if (d->copy_out) cudaStreamDestroy(d->copy_out);
@@ -283,6 +288,47 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
         cin[0] = si;
         cout[0] = so;
     }
+    // Progressive read-back.  Streams of a chunk advance together, so their output can leave
+    // the device while they are still being decoded: when a chunk's outputs are rows of one
+    // pitch and one capacity (the layout of a block codec), the kernel counts, per mark, the
+    // streams whose output below that mark is complete (DecodeArgs::progress, in pinned host
+    // memory), and this thread issues one strided copy per (chunk, mark) as the counts fill up.
+    // Other layouts are copied chunk by chunk after their kernel.
+    constexpr uint32_t kMarks = 8;
+    struct Rows {
+        bool on = false;
+        uint64_t pitch = 0, cap = 0;
+        uint32_t step = 0, marks = 0, issued = 0;
+    };
+    std::vector<Rows> rows(n_chunks);
+    uint32_t pending_marks = 0;
+    for (uint32_t c = 0; c < n_chunks && ordered; c++) {
+        const uint32_t s0 = first[c], cnt = first[c + 1] - s0;
+        if (cnt == 0) continue;
+        Rows r;
+        r.cap = out_cap[s0];
+        r.pitch = cnt > 1 ? out_off[s0 + 1] - out_off[s0] : r.cap;
+        r.on = r.cap >= (64u << 10) && r.cap < (1ull << 31) && r.pitch >= r.cap;
+        for (uint32_t i = 1; i < cnt && r.on; i++)
+            r.on = out_cap[s0 + i] == r.cap && out_off[s0 + i] == out_off[s0] + (uint64_t)i * r.pitch;
+        if (!r.on) continue;
+        r.step = (uint32_t)(((r.cap + kMarks - 1) / kMarks + 511) & ~(uint64_t)511);
+        r.marks = (uint32_t)((r.cap + r.step - 1) / r.step);
+        pending_marks += r.marks;
+        rows[c] = r;
+    }
+    CUDA_TRY(d->h_progress.reserve((size_t)n_chunks * kMarks * sizeof(uint32_t)));
+    volatile uint32_t* prog = (volatile uint32_t*)d->h_progress.p;
+    memset(d->h_progress.p, 0, (size_t)n_chunks * kMarks * sizeof(uint32_t));
+    auto copy_mark = [&](uint32_t c, uint32_t m) {  // output columns [m * step, (m + 1) * step) of every row of chunk c
+        const Rows& r = rows[c];
+        const uint32_t s0 = first[c], cnt = first[c + 1] - s0;
+        const uint64_t col = (uint64_t)m * r.step;
+        const uint64_t width = r.cap - col < r.step ? r.cap - col : r.step;
+        return cudaMemcpy2DAsync(out + out_off[s0] + col, r.pitch, d_out + (out_off[s0] - so.lo) + col, r.pitch, width, cnt,
+                                 cudaMemcpyDeviceToHost, d->copy_out);
+    };
+
     CUDA_TRY(d->ctrl.reserve(64 * sizeof(uint32_t)));
     CUDA_TRY(cudaMemsetAsync(d->ctrl.p, 0, 64 * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemcpyAsync(dm, hm, (size_t)n * 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -308,14 +354,45 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
         cudaStreamWaitEvent(ks, ev_in[c], 0);
         rc = dec_enqueue(d, d_in, dm + s0, dm + n + s0, cnt, d_out, dm + 2 * (size_t)n + s0, dm + 3 * (size_t)n + s0,
                          dm + 4 * (size_t)n + s0, (int32_t*)(dm + 5 * (size_t)n) + s0, max_lclp1, mode,
-                         (uint32_t*)d->ctrl.p + c, ks, c % n_k, n_k);
+                         (uint32_t*)d->ctrl.p + c, ks, c % n_k, n_k, rows[c].on ? (uint32_t*)d->h_progress.p + c * kMarks : nullptr,
+                         rows[c].marks, rows[c].step);
         if (rc != LZB_OK) break;
         cudaEventRecord(ev_k[c], ks);
-        cudaStreamWaitEvent(d->copy_out, ev_k[c], 0);
         cudaStreamWaitEvent(st, ev_k[c], 0);  // the out_len / status read-back below follows every kernel
-        if (cout[c].hi > cout[c].lo)
+        if (!rows[c].on && cout[c].hi > cout[c].lo) {
+            cudaStreamWaitEvent(d->copy_out, ev_k[c], 0);
             err = cudaMemcpyAsync(out + cout[c].lo, d_out + (cout[c].lo - so.lo), cout[c].hi - cout[c].lo, cudaMemcpyDeviceToHost,
                                   d->copy_out);
+        }
+    }
+    // follow the progress counters of the row-shaped chunks
+    for (uint32_t idle = 0; pending_marks && rc == LZB_OK && err == cudaSuccess;) {
+        bool moved = false;
+        for (uint32_t c = 0; c < n_events && err == cudaSuccess; c++) {
+            Rows& r = rows[c];
+            while (r.on && r.issued < r.marks && prog[c * kMarks + r.issued] >= first[c + 1] - first[c] && err == cudaSuccess) {
+                err = copy_mark(c, r.issued++);
+                pending_marks--;
+                moved = true;
+            }
+        }
+        if (moved) {
+            idle = 0;
+        } else if (++idle % 256 == 0) {
+            // nothing new: if every kernel is gone (finished, or failed) the counters are final
+            bool running = false;
+            for (uint32_t k = 0; k < n_k; k++) running = running || cudaStreamQuery(d->kstream[k]) == cudaErrorNotReady;
+            if (!running) break;
+        } else {
+            std::this_thread::yield();
+        }
+    }
+    // whatever the loop did not see (a kernel that failed, or counters read just before the kernels ended)
+    for (uint32_t c = 0; c < n_events && rc == LZB_OK && err == cudaSuccess; c++) {
+        Rows& r = rows[c];
+        if (!r.on || r.issued == r.marks) continue;
+        cudaStreamWaitEvent(d->copy_out, ev_k[c], 0);
+        while (r.issued < r.marks && err == cudaSuccess) err = copy_mark(c, r.issued++);
     }
     if (rc == LZB_OK && err == cudaSuccess)
         err = cudaMemcpyAsync(hm + 4 * (size_t)n, dm + 4 * (size_t)n, (size_t)n * (sizeof(uint64_t) + sizeof(int32_t)),

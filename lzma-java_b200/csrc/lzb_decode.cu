@@ -169,7 +169,9 @@ struct RangeDec {
 #pragma unroll 1
             do {
                 range >>= 1;
-                const bool one = code >= range;
+                // the reference tests the SIGN of code - range (:31-32); on a corrupt stream, where
+                // code may exceed range by 2^31 or more, that is not the unsigned comparison
+                const bool one = (int32_t)(code - range) >= 0;
                 if (one) code -= range;
                 result += result;
                 if (one) result++;
@@ -296,6 +298,15 @@ __device__ __forceinline__ uint32_t decode_literal_g(RangeDec& rd, uint16_t* pro
 
 enum : int { EV_MATCH = 0, EV_DONE = 1, EV_DATA_ERROR = 2, EV_CAPACITY = 3 };
 
+// DecodeArgs::progress: every lane publishes its own output stores system-wide, then lane 0 counts
+// the stream in for marks [from, to).
+__device__ __forceinline__ void report_progress(const DecodeArgs& a, uint32_t from, uint32_t to, int lane) {
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0)
+        for (uint32_t m = from; m < to; m++) atomicAdd_system(a.progress + m, 1u);
+}
+
 template <int MODE>
 __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, uint16_t* lit_global, int lane) {
     const uint64_t in_len = a.in_len[s];
@@ -306,6 +317,7 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
     // LzmaAlone.java:220-236 -- 5 property bytes + LE64 size; Decoder.java:303-318
     int status = 1;
     uint32_t pos = 0;
+    uint32_t marks_done = 0;  // progress marks already reported for this stream
     if (in_len < LZB_KERNEL_HEADER) {
         status = 0;  // "input .lzma file is too short" / "Can't read stream size"
     } else if (in_len - LZB_KERNEL_HEADER >= 0xFFFFFFF0ull || cap64 >= 0xFFFFFFF0ull) {
@@ -447,6 +459,13 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
                 const uint32_t len = evlen >> 2;
                 const uint32_t d = __shfl_sync(kFull, rep0, 0) + 1;
                 pos = __shfl_sync(kFull, pos, 0);
+                if (a.progress && marks_done + 1 < a.marks && pos >= (marks_done + 1) * a.mark_step) {
+                    // everything below `pos` is stored (the pending tail went out above)
+                    uint32_t reached = pos / a.mark_step;
+                    if (reached > a.marks - 1) reached = a.marks - 1;
+                    report_progress(a, marks_done, reached, lane);
+                    marks_done = reached;
+                }
                 __syncwarp();  // order earlier stores (lane 0's literals, other lanes' copies) before these loads
                 const uint8_t* src = out + pos - d;
                 uint8_t* dst = out + pos;
@@ -480,6 +499,7 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
         a.out_len[s] = pos;
         a.status[s] = status;
     }
+    if (a.progress) report_progress(a, marks_done, a.marks, lane);
 }
 
 template <int MODE>

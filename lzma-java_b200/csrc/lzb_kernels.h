@@ -42,6 +42,12 @@ struct DecodeArgs {
     uint32_t* ticket;        // zeroed before launch
     uint16_t* lit_scratch;   // literal tables kept in global memory (kDecHybrid, kDecGlobal)
     size_t lit_stride;       // in 16-bit slots, per resident stream
+    // Optional progress report for a host that copies output back while the kernel still runs:
+    // progress[m] counts the streams whose output below (m + 1) * mark_step bytes is complete and
+    // visible system-wide; the last counter (m = marks - 1) counts finished streams.
+    uint32_t* progress = nullptr;  // pinned host memory (device-accessible), zeroed before launch
+    uint32_t marks = 0;
+    uint32_t mark_step = 0;
 };
 
 // header pre-pass over well-formed streams: d_max_lclp1[0] = max(lc + lp + 1) (0 if there is none), [1] = max(pb + 1)

@@ -171,3 +171,38 @@ def test_decode_many_streams(lzb, oracle, corpus):
     assert (status == 1).all() and (out_len == 4096).all()
     got = out.reshape(n, 4096 + 273)[:, :4096].reshape(-1)
     assert np.array_equal(got, data)
+
+
+def test_decode_progressive_readback(lzb, oracle, corpus):
+    """Row-shaped outputs of >= 64 KiB take the progressive read-back of lzb_dec_code_batch (strided
+    copies issued while the kernels run, driven by the kernel's progress counters).  Streams that
+    end early (corrupt, truncated, bad header, capacity) must not stall it, and every byte the
+    oracle's decoder writes must arrive."""
+    n, size = 1300, 70000
+    data = corpus.generate(size, n, corpus.MIXED, 21)
+    off = np.arange(n, dtype=np.uint64) * size
+    ln = np.full(n, size, dtype=np.uint64)
+    comp, coff, clen = oracle.encode_batch(data, off, ln, oracle.props(**BASE), with_header=True, threads=8)
+    comp = comp.copy()
+    rng = np.random.default_rng(99)
+    for i in rng.choice(n, 40, replace=False):      # flipped payload bytes
+        comp[int(coff[i]) + 13 + int(rng.integers(0, int(clen[i]) - 13))] ^= 1 << int(rng.integers(0, 8))
+    clen = clen.copy()
+    for i in rng.choice(n, 20, replace=False):      # truncated
+        clen[i] = clen[i] // 2
+    comp[int(coff[7])] = 225                        # pb = 5
+    clen[11] = 5                                    # shorter than the header
+    pitch = size + 273 + 15
+    cap = np.full(n, size + 273, dtype=np.uint64)
+    ooff = np.arange(n, dtype=np.uint64) * pitch
+    ref_out, ref_len, ref_status = oracle.decode_batch(comp, coff, clen, ooff, cap, threads=8)
+    dec = lzb.Decoder()
+    out, out_len, status = dec.code_batch(comp, coff, clen, ooff, cap)
+    dec.close()
+    ref_status = np.where(ref_status < 0, lzb.LZB_E_CAPACITY, ref_status)
+    assert np.array_equal(status, ref_status)
+    assert np.array_equal(out_len, ref_len)
+    assert (status == 1).sum() > n - 80
+    for i in range(n):
+        a, b = int(ooff[i]), int(ooff[i]) + int(out_len[i])
+        assert np.array_equal(out[a:b], ref_out[a:b]), i
