@@ -262,10 +262,16 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
     uint8_t* d_in = (uint8_t*)d->d_in.p;
     uint8_t* d_out = (uint8_t*)d->d_out.p;
 
-    // The batch is cut into chunks of about 7 streams per SM, each with its own input copy,
-    // kernel launch and output copy.  The kernels go round-robin over up to four streams so that
-    // chunks share the SMs (4 x 7 warps = the residency of one big launch) while the input of
-    // later chunks and the output of earlier ones are still on the PCIe bus.
+    // Two ways to keep the PCIe bus busy while the kernels run.
+    // (a) Row-shaped output (every stream the same capacity, >= 64 KiB, at one pitch: a block
+    //     codec's layout): ONE launch for the whole batch, and the output is read back
+    //     progressively behind the decoders (see below).  Cutting such a batch into chunks was
+    //     measured to lose: co-resident chunks share the issue slots, so a chunk that starts late
+    //     finishes late and runs its tail on a mostly idle GPU (4096 x 256 KiB: 1 chunk 10.8 GB/s,
+    //     2 chunks 10.5, 4 chunks 10.0).
+    // (b) Any other layout: chunks of about 7 streams per SM, each with its own input copy, kernel
+    //     launch and output copy; the kernels go round-robin over up to four streams so that four
+    //     chunks share the SMs (4 x 7 warps = the residency of one big launch).
     const int mode = pick_dec_mode(max_lclp1, max_pb1, n, d->num_sms);
     const uint32_t n_k = mode == lzb::kDecGlobal ? 1u : 4u;  // kDecGlobal: scratch can be GBs, one launch at a time
     for (uint32_t k = 0; k < n_k; k++)
@@ -273,6 +279,16 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
     const uint32_t per_chunk = (uint32_t)d->num_sms * 7;
     uint32_t n_chunks = (n + per_chunk - 1) / per_chunk;
     if (n_chunks > 16) n_chunks = 16;
+    {
+        bool whole = out_cap[0] >= (64u << 10);
+        const uint64_t pitch = n > 1 ? out_off[1] - out_off[0] : out_cap[0];
+        for (uint32_t i = 1; i < n && whole; i++) whole = out_cap[i] == out_cap[0] && out_off[i] == out_off[0] + (uint64_t)i * pitch;
+        if (whole) n_chunks = 1;
+    }
+    if (const char* e = getenv("LZB_DEC_CHUNKS")) {  // test hook
+        const int v = atoi(e);
+        if (v >= 1 && v <= 16 && (uint32_t)v <= n) n_chunks = (uint32_t)v;
+    }
     std::vector<uint32_t> first(n_chunks + 1);
     std::vector<Span> cin(n_chunks), cout(n_chunks);
     for (uint32_t c = 0; c <= n_chunks; c++) first[c] = (uint32_t)((uint64_t)n * c / n_chunks);
@@ -294,7 +310,12 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
     // streams whose output below that mark is complete (DecodeArgs::progress, in pinned host
     // memory), and this thread issues one strided copy per (chunk, mark) as the counts fill up.
     // Other layouts are copied chunk by chunk after their kernel.
-    constexpr uint32_t kMarks = 8;
+    constexpr uint32_t kMaxMarks = 32;
+    uint32_t kMarks = 8;
+    if (const char* e = getenv("LZB_DEC_MARKS")) {  // test hook
+        const int v = atoi(e);
+        if (v >= 1 && v <= (int)kMaxMarks) kMarks = (uint32_t)v;
+    }
     struct Rows {
         bool on = false;
         uint64_t pitch = 0, cap = 0;
@@ -317,9 +338,9 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
         pending_marks += r.marks;
         rows[c] = r;
     }
-    CUDA_TRY(d->h_progress.reserve((size_t)n_chunks * kMarks * sizeof(uint32_t)));
+    CUDA_TRY(d->h_progress.reserve((size_t)n_chunks * kMaxMarks * sizeof(uint32_t)));
     volatile uint32_t* prog = (volatile uint32_t*)d->h_progress.p;
-    memset(d->h_progress.p, 0, (size_t)n_chunks * kMarks * sizeof(uint32_t));
+    memset(d->h_progress.p, 0, (size_t)n_chunks * kMaxMarks * sizeof(uint32_t));
     auto copy_mark = [&](uint32_t c, uint32_t m) {  // output columns [m * step, (m + 1) * step) of every row of chunk c
         const Rows& r = rows[c];
         const uint32_t s0 = first[c], cnt = first[c + 1] - s0;

@@ -307,7 +307,7 @@ __device__ __forceinline__ void report_progress(const DecodeArgs& a, uint32_t fr
         for (uint32_t m = from; m < to; m++) atomicAdd_system(a.progress + m, 1u);
 }
 
-template <int MODE>
+template <int MODE, bool PROGRESS>
 __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, uint16_t* lit_global, int lane) {
     const uint64_t in_len = a.in_len[s];
     const uint8_t* in = a.in + a.in_off[s];
@@ -459,7 +459,7 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
                 const uint32_t len = evlen >> 2;
                 const uint32_t d = __shfl_sync(kFull, rep0, 0) + 1;
                 pos = __shfl_sync(kFull, pos, 0);
-                if (a.progress && marks_done + 1 < a.marks && pos >= (marks_done + 1) * a.mark_step) {
+                if (PROGRESS && marks_done + 1 < a.marks && pos >= (marks_done + 1) * a.mark_step) {
                     // everything below `pos` is stored (the pending tail went out above)
                     uint32_t reached = pos / a.mark_step;
                     if (reached > a.marks - 1) reached = a.marks - 1;
@@ -499,10 +499,10 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
         a.out_len[s] = pos;
         a.status[s] = status;
     }
-    if (a.progress) report_progress(a, marks_done, a.marks, lane);
+    if (PROGRESS) report_progress(a, marks_done, a.marks, lane);
 }
 
-template <int MODE>
+template <int MODE, bool PROGRESS>
 __global__ void __launch_bounds__(dec_mode_warps(MODE) * 32, 1) lzb_decode_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) uint16_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(dec_mode_warps(MODE) * 32, 1) lzb_decode_kerne
     const uint32_t slots = gridDim.x * (blockDim.x >> 5);
     uint32_t s = (uint32_t)warp * gridDim.x + blockIdx.x;
     while (s < a.n) {
-        decode_stream<MODE>(a, s, model, lit_global, lane);
+        decode_stream<MODE, PROGRESS>(a, s, model, lit_global, lane);
         if (lane == 0) s = slots + atomicAdd(a.ticket, 1u);
         s = __shfl_sync(kFull, s, 0);
     }
@@ -549,8 +549,10 @@ cudaError_t launch_decode(const DecodeArgs& a, int mode, int num_sms, cudaStream
     // streams are handed out by ticket, so spread the warps over every SM (4096 streams: 148 CTAs
     // of 28 warps with 48 idle warps, not 147 full CTAs and an idle SM)
     const int grid = a.n < (uint32_t)num_sms ? (int)a.n : num_sms;
-    auto kern = mode == kDecSmem ? lzb_decode_kernel<kDecSmem>
-                                 : mode == kDecHybrid ? lzb_decode_kernel<kDecHybrid> : lzb_decode_kernel<kDecGlobal>;
+    const bool prog = a.progress != nullptr;  // the reporting variant only when somebody listens
+    auto kern = mode == kDecSmem     ? (prog ? lzb_decode_kernel<kDecSmem, true> : lzb_decode_kernel<kDecSmem, false>)
+                : mode == kDecHybrid ? (prog ? lzb_decode_kernel<kDecHybrid, true> : lzb_decode_kernel<kDecHybrid, false>)
+                                     : (prog ? lzb_decode_kernel<kDecGlobal, true> : lzb_decode_kernel<kDecGlobal, false>);
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(max_warps * slice));
     if (err != cudaSuccess) return err;
     kern<<<grid, warps * 32, (size_t)warps * slice, st>>>(a);

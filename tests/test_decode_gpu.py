@@ -173,11 +173,15 @@ def test_decode_many_streams(lzb, oracle, corpus):
     assert np.array_equal(got, data)
 
 
-def test_decode_progressive_readback(lzb, oracle, corpus):
+@pytest.mark.parametrize("chunks", [None, "3"])
+def test_decode_progressive_readback(lzb, oracle, corpus, chunks, monkeypatch):
     """Row-shaped outputs of >= 64 KiB take the progressive read-back of lzb_dec_code_batch (strided
     copies issued while the kernels run, driven by the kernel's progress counters).  Streams that
     end early (corrupt, truncated, bad header, capacity) must not stall it, and every byte the
-    oracle's decoder writes must arrive."""
+    oracle's decoder writes must arrive.  One launch by default; LZB_DEC_CHUNKS=3 runs three chunks
+    with a progress row each."""
+    if chunks:
+        monkeypatch.setenv("LZB_DEC_CHUNKS", chunks)
     n, size = 1300, 70000
     data = corpus.generate(size, n, corpus.MIXED, 21)
     off = np.arange(n, dtype=np.uint64) * size
