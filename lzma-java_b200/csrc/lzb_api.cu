@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -399,13 +400,13 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
         }
         if (moved) {
             idle = 0;
-        } else if (++idle % 256 == 0) {
+        } else if (++idle % 64 == 0) {
             // nothing new: if every kernel is gone (finished, or failed) the counters are final
             bool running = false;
             for (uint32_t k = 0; k < n_k; k++) running = running || cudaStreamQuery(d->kstream[k]) == cudaErrorNotReady;
             if (!running) break;
         } else {
-            std::this_thread::yield();
+            std::this_thread::sleep_for(std::chrono::microseconds(50));  // marks are milliseconds apart
         }
     }
     // whatever the loop did not see (a kernel that failed, or counters read just before the kernels ended)
