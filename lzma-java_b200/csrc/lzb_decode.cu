@@ -267,14 +267,18 @@ __device__ __forceinline__ uint32_t decode_literal_matched_s(RangeDec& rd, uint3
 }
 // kDecHybrid: the matched tables (indices 0x100..0x2FF of a coder) are `gprobs` in global memory,
 // 0x200 slots per coder; once a bit disagrees with the match byte the walk continues in the
-// coder's normal tree in shared memory (0x100 slots per coder at `sprobs`).
-__device__ __forceinline__ uint32_t decode_literal_matched_h(RangeDec& rd, uint32_t sprobs, uint16_t* gprobs, uint32_t match_byte) {
+// coder's normal tree in shared memory (0x100 slots per coder at `sprobs`).  Most matched
+// literals part from their match byte within a few bits, so the top three levels of the matched
+// trees (symbol < 8: 16 slots per coder at `stop`, index (matchBit << 3) + symbol) stay in shared
+// memory as well and only the deeper, rarer nodes cost an L2 round trip.
+__device__ __forceinline__ uint32_t decode_literal_matched_h(RangeDec& rd, uint32_t sprobs, uint32_t stop, uint16_t* gprobs,
+                                                             uint32_t match_byte) {
     uint32_t symbol = 1;
 #pragma unroll 1
     do {
         match_byte <<= 1;
         const uint32_t mb = match_byte & 0x100u;
-        const uint32_t b = rd.bit_g(gprobs + mb + symbol);
+        const uint32_t b = symbol < 8 ? rd.bit_s(stop + 2 * ((mb >> 5) + symbol)) : rd.bit_g(gprobs + mb + symbol);
         symbol = (symbol << 1) | b;
         if ((mb >> 8) != b) break;
     } while (symbol < 0x100);
@@ -334,7 +338,7 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
         // arithmetic); SetDictionarySize (:160-170) rejects a negative size.
         const ModelLayout L = make_layout(lc, lp, pb);
         // literal slots in shared / global memory for this mode
-        const int n_lit_s = MODE == kDecSmem ? L.n_literal : MODE == kDecHybrid ? 0x100 << (lc + lp) : 0;
+        const int n_lit_s = MODE == kDecSmem ? L.n_literal : MODE == kDecHybrid ? 0x110 << (lc + lp) : 0;  // hybrid: normal trees + matched tops
         const int n_lit_g = MODE == kDecSmem ? 0 : MODE == kDecHybrid ? 0x200 << (lc + lp) : L.n_literal;
         if (pb > 4 || (int32_t)dict < 0) {
             status = 0;
@@ -375,7 +379,8 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
                                 prev_byte = state >= 7 ? decode_literal_matched_s(rd, sprobs, match_byte) : decode_literal_s(rd, sprobs);
                             } else if (MODE == kDecHybrid) {
                                 const uint32_t sprobs = sm + 2 * (L.literal + 0x100u * ctx);
-                                prev_byte = state >= 7 ? decode_literal_matched_h(rd, sprobs, lit_global + 0x200u * ctx, match_byte)
+                                const uint32_t stop = sm + 2 * (L.literal + (0x100u << (lc + lp)) + 16u * ctx);
+                                prev_byte = state >= 7 ? decode_literal_matched_h(rd, sprobs, stop, lit_global + 0x200u * ctx, match_byte)
                                                        : decode_literal_s(rd, sprobs);
                             } else {
                                 prev_byte = decode_literal_g(rd, lit_global + 0x300u * ctx, state >= 7, match_byte);

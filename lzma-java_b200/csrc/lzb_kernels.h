@@ -19,13 +19,13 @@ namespace lzb {
 // almost doubles the resident streams.  It pays when there are more streams than kDecSmem slots.
 enum DecMode : int {
     kDecSmem = 0,    // whole model in shared memory (lc + lp <= 3)
-    kDecHybrid = 1,  // matched-literal tables in global memory (lc + lp <= 3)
+    kDecHybrid = 1,  // matched-literal tables in global memory, except their top three levels (lc + lp <= 3)
     kDecGlobal = 2,  // all literal tables in global memory (any lc, lp)
 };
 constexpr int kDecMaxWarps = 15;          // streams resident per SM, kDecSmem / kDecGlobal
 constexpr size_t kDecSliceBytes = 15488;  // 15 * 15488 = 232 320 B <= 227 KB per CTA
 constexpr int kDecHybridWarps = 28;       // 28 warps * 72 registers fill the register file
-constexpr size_t kDecHybridSlice = 7808;  // fixed part (pb = 4: 3696 B) + 8 normal literal trees (4096 B)
+constexpr size_t kDecHybridSlice = 8064;  // fixed part (pb = 4: 3696 B) + 8 normal literal trees (4096 B) + top of the matched trees (256 B)
 __host__ __device__ constexpr int dec_mode_warps(int mode) { return mode == kDecHybrid ? kDecHybridWarps : kDecMaxWarps; }
 __host__ __device__ constexpr size_t dec_mode_slice(int mode) { return mode == kDecHybrid ? kDecHybridSlice : kDecSliceBytes; }
 
