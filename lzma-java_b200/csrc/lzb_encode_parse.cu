@@ -1298,6 +1298,9 @@ __device__ __forceinline__ void Enc::run() {
 __global__ void __launch_bounds__(kEncMaxWarps * 32, 1) lzb_parse_kernel(ParseArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CtaTables* tables = reinterpret_cast<CtaTables*>(smem_raw);
+    // the pipelined path launches without asking the host first: lists that did not fit their
+    // pair slots are incomplete, the host redoes such a group with more room
+    if (*a.mf.overflow) return;
     init_cta_tables(tables);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;
@@ -1407,6 +1410,9 @@ size_t parse_opt_bytes_per_slot() { return sizeof(OptNode) * (size_t)kNumOpts; }
 cudaError_t launch_parse(const ParseArgs& a, int grid, int warps, cudaStream_t st) {
     const size_t smem = sizeof(CtaTables) + (size_t)warps * a.slice_bytes;
     cudaError_t e = cudaFuncSetAttribute(lzb_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    // small CTAs (one warp each on the pipelined path) must still fill the SM's shared memory
+    e = cudaFuncSetAttribute(lzb_parse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     lzb_parse_kernel<<<grid, warps * 32, smem, st>>>(a);
     return cudaGetLastError();

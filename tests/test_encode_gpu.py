@@ -189,6 +189,23 @@ def test_encode_many_tiny_blocks_and_pair_overflow_retry(lzb, oracle, corpus, mo
     _check(lzb, oracle, BASE, text)
 
 
+def test_encode_pipelined_groups_over_lanes(lzb, oracle, corpus, monkeypatch):
+    """Batches with more blocks than resident parser slots flow through lanes in groups (lzb_encode.cu,
+    run_pipelined); forced here on a small batch: ragged last group, more groups than lanes, every block == oracle."""
+    monkeypatch.setenv("LZB_ENC_PIPE", "1")
+    monkeypatch.setenv("LZB_ENC_GROUP", "3")
+    monkeypatch.setenv("LZB_ENC_LANES", "2")
+    blocks = [corpus.generate(3000 + 977 * i, 1, i % 4, 29, i).tobytes() for i in range(17)] + [b"", b"z"]
+    _check(lzb, oracle, BASE, blocks)
+    p = dict(BASE)
+    p.update(fb=64, lc=4, lp=4, pb=3)  # literal coder in global memory: one slot per CTA of the group
+    _check(lzb, oracle, p, blocks[:7])
+    # groups whose match lists overflow their pair slots are skipped on the device and redone afterwards
+    monkeypatch.setenv("LZB_PAIR_MUL", "1")
+    text = [corpus.generate(20000, 1, k % 2, 30, k).tobytes() for k in range(8)]
+    _check(lzb, oracle, BASE, text)
+
+
 @pytest.mark.parametrize("kw", [{}, {"fb": 64}, {"fb": 273, "dict_size": 1 << 23}, {"mf": 0}, {"dict_size": 4096}, {"dict_size": 1}])
 def test_match_finder_lists_equal_the_instrumented_trace(lzb, oracle, corpus, kw):
     """North-star subsystem 1: the per-position (length, distance) lists of the parallel bt4/bt2
