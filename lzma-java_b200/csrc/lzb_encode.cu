@@ -3,9 +3,9 @@
 // Replaces Encoder.Code (LZMA/Encoder.java:1064-1077) for a batch of
 // independent blocks.  Per wave of blocks:  memset(heads, next, counters) ->
 // lzb_mf_link_kernel -> lzb_mf_tree_kernel -> lzb_mf_long_kernel -> lzb_parse_kernel.
-// A batch that fits the resident parser slots is one wave (run_waves); a larger one is cut into
-// groups that flow through several lanes (run_pipelined) so that parser slots never sit idle
-// behind a wave's slowest block and the match finder overlaps the parsers.
+// A wave holds as many blocks as the memory budget allows; when it holds more blocks than the
+// parser has resident slots, the parser takes them longest-expected-first (most match pairs
+// first), so the wave does not end on a late-started slow block.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -46,46 +46,60 @@ uint32_t hash_stride_for(int32_t dict, bool bt4, uint32_t* mask_out) {  // BinTr
     return hs + 1 + kHash2Size + kHash3Size;
 }
 
-// carve all scratch for a wave of `wb` blocks; with base == nullptr only sizes are computed
-size_t carve(uint8_t* base, uint32_t wb, uint32_t np, uint32_t hash_stride, uint32_t pair_cap, size_t slots, size_t lit_slots,
-             MfWave* w, ParseArgs* pa, uint32_t** ctrl) {
+// Scratch comes in two parts with different lifetimes.  The match-finder part (hash heads, bucket
+// links, candidate arrays, tree) is dead once the lists are written; the list part (per-position
+// lists, parser spill space) lives until the parse of its blocks has finished.
+// With base == nullptr only sizes are computed.  *zero_len = bytes at the start of the part that
+// must be zero before the match finder runs.
+size_t carve_mf(uint8_t* base, uint32_t wb, uint32_t np, uint32_t hash_stride, MfWave* w, size_t* zero_len) {
     Carver c{base};
-    uint32_t* ctl = c.take<uint32_t>(64);                  // [0] parser ticket, [1] pair overflow
-    uint32_t* pair_used = c.take<uint32_t>(wb);
+    uint32_t* ctl = c.take<uint32_t>(64);                  // [0] long-bucket count, [1] long-bucket ticket
     uint32_t* heads = c.take<uint32_t>((size_t)wb * hash_stride);
     uint32_t* next = c.take<uint32_t>((size_t)wb * np);
-    const size_t zero_end = c.off;                          // everything above is zeroed per wave
+    if (zero_len) *zero_len = c.off;
     uint32_t* prev2 = c.take<uint32_t>((size_t)wb * np);
     uint32_t* prev3 = c.take<uint32_t>((size_t)wb * np);
     uint32_t* son = c.take<uint32_t>((size_t)wb * 2 * np);
-    uint32_t* idx = c.take<uint32_t>((size_t)wb * np);
-    uint32_t* pairs = c.take<uint32_t>((size_t)wb * pair_cap + 64);   // + slack: the parser prefetches 32 slots blindly
-    uint16_t* pairs2 = c.take<uint16_t>((size_t)wb * pair_cap + 64);
     uint4* long_items = c.take<uint4>((size_t)wb * (np / kLongChain + 1));  // a block has at most n / kLongChain long buckets
-    void* opt = c.take<uint8_t>(slots * parse_opt_bytes_per_slot());
-    uint16_t* lit = c.take<uint16_t>(lit_slots);
     if (w) {
         w->heads = heads;
         w->next = next;
         w->prev2 = prev2;
         w->prev3 = prev3;
         w->son = son;
+        w->long_count = ctl;
+        w->long_ticket = ctl + 1;
+        w->long_items = long_items;
+    }
+    return (c.off + 255) & ~size_t(255);
+}
+
+size_t carve_lists(uint8_t* base, uint32_t wb, uint32_t np, uint32_t pair_cap, size_t slots, size_t lit_slots, MfWave* w,
+                   ParseArgs* pa, size_t* zero_len, uint32_t** order_out = nullptr) {
+    Carver c{base};
+    uint32_t* ctl = c.take<uint32_t>(64);                  // [0] parser ticket, [1] pair overflow
+    uint32_t* pair_used = c.take<uint32_t>(wb);
+    if (zero_len) *zero_len = c.off;
+    uint32_t* order = c.take<uint32_t>(wb);                // the parser's block order (run_waves)
+    if (order_out) *order_out = order;
+    uint32_t* idx = c.take<uint32_t>((size_t)wb * np);
+    uint32_t* pairs = c.take<uint32_t>((size_t)wb * pair_cap + 64);   // + slack: the parser prefetches 32 slots blindly
+    uint16_t* pairs2 = c.take<uint16_t>((size_t)wb * pair_cap + 64);
+    void* opt = c.take<uint8_t>(slots * parse_opt_bytes_per_slot());
+    uint16_t* lit = c.take<uint16_t>(lit_slots);
+    if (w) {
         w->idx = idx;
         w->pairs = pairs;
         w->pairs2 = pairs2;
         w->pair_used = pair_used;
         w->overflow = ctl + 1;
-        w->long_count = ctl + 2;
-        w->long_ticket = ctl + 3;
-        w->long_items = long_items;
     }
     if (pa) {
         pa->ticket = ctl;
         pa->opt_scratch = opt;
         pa->lit_scratch = lit;
     }
-    if (ctrl) *ctrl = reinterpret_cast<uint32_t*>(zero_end);  // smuggles the zeroed prefix length
-    return c.off;
+    return (c.off + 255) & ~size_t(255);
 }
 
 // ---- what a batch has in common ----------------------------------------------------------
@@ -97,12 +111,11 @@ struct Plan {
     bool timing;
 };
 
-// MfWave + ParseArgs for blocks [first, first + wb) over the scratch set at `base`
-void bind_wave(const EncodeArgs& a, const Plan& P, uint8_t* base, uint32_t first, uint32_t wb, uint32_t pair_cap, size_t slots,
-               MfWave* w, ParseArgs* pa, size_t* zero_len) {
-    uint32_t* zero_len_ptr = nullptr;
-    carve(base, wb, P.np, P.hash_stride, pair_cap, slots, slots * P.lit_per_slot, w, pa, &zero_len_ptr);
-    *zero_len = reinterpret_cast<size_t>(zero_len_ptr);
+// MfWave + ParseArgs for blocks [first, first + wb): match-finder scratch at `mf_base`, lists at `list_base`
+void bind_wave(const EncodeArgs& a, const Plan& P, uint8_t* mf_base, uint8_t* list_base, uint32_t first, uint32_t wb,
+               uint32_t pair_cap, size_t slots, MfWave* w, ParseArgs* pa, size_t* mf_zero, size_t* list_zero, uint32_t** order) {
+    carve_mf(mf_base, wb, P.np, P.hash_stride, w, mf_zero);
+    carve_lists(list_base, wb, P.np, pair_cap, slots, slots * P.lit_per_slot, w, pa, list_zero, order);
     w->in = a.in;
     w->in_off = a.in_off + first;
     w->in_len = a.in_len + first;
@@ -157,24 +170,39 @@ cudaError_t run_waves(const EncodeArgs& a, const Plan& P, EncScratch& scratch, i
     uint32_t done = 0;
     while (done < count) {
         const uint32_t pair_cap = pair_cap_for(pair_mul, a.max_in_len);
-        // largest wave that fits the budget
+        // largest wave that fits the budget, the remaining blocks spread evenly over the waves still to come
         uint32_t wb = std::min<uint32_t>(count - done, 32768);
-        while (wb > 1 && carve(nullptr, wb, P.np, P.hash_stride, pair_cap, slots, slots * P.lit_per_slot, nullptr, nullptr, nullptr) > budget)
-            wb = (wb + 1) / 2;
-        const size_t need = carve(nullptr, wb, P.np, P.hash_stride, pair_cap, slots, slots * P.lit_per_slot, nullptr, nullptr, nullptr);
-        e = grow(scratch, need, st);
+        auto wave_bytes = [&](uint32_t blocks) {
+            return carve_mf(nullptr, blocks, P.np, P.hash_stride, nullptr, nullptr) +
+                   carve_lists(nullptr, blocks, P.np, pair_cap, slots, slots * P.lit_per_slot, nullptr, nullptr, nullptr);
+        };
+        if (wave_bytes(wb) > budget) {
+            uint32_t lo = 1, hi = wb;  // wave_bytes is monotonic: binary search the largest count that fits
+            while (lo < hi) {
+                const uint32_t mid = lo + (hi - lo + 1) / 2;
+                if (wave_bytes(mid) <= budget) lo = mid;
+                else hi = mid - 1;
+            }
+            const uint32_t left = count - done, waves = (left + lo - 1) / lo;
+            wb = (left + waves - 1) / waves;
+        }
+        e = grow(scratch, wave_bytes(wb), st);
         if (e != cudaSuccess) return e;
         MfWave w;
         ParseArgs pa;
-        size_t zero_len = 0;
-        bind_wave(a, P, (uint8_t*)scratch.p, first + done, wb, pair_cap, slots, &w, &pa, &zero_len);
+        size_t mf_zero = 0, list_zero = 0;
+        uint8_t* list_base = (uint8_t*)scratch.p + carve_mf(nullptr, wb, P.np, P.hash_stride, nullptr, nullptr);
+        uint32_t* order_dev = nullptr;
+        bind_wave(a, P, (uint8_t*)scratch.p, list_base, first + done, wb, pair_cap, slots, &w, &pa, &mf_zero, &list_zero, &order_dev);
         // LZB_ENC_TIMING=1 (developer hook): phase times of every wave on stderr
         cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};
         if (P.timing) {
             for (auto& x : tev) cudaEventCreate(&x);
             cudaEventRecord(tev[0], st);
         }
-        e = cudaMemsetAsync(scratch.p, 0, zero_len, st);
+        e = cudaMemsetAsync(scratch.p, 0, mf_zero, st);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(list_base, 0, list_zero, st);
         if (e != cudaSuccess) return e;
         e = launch_mf(w, (uint32_t)a.max_in_len, num_sms, st);
         if (e != cudaSuccess) return e;
@@ -211,6 +239,28 @@ cudaError_t run_waves(const EncodeArgs& a, const Plan& P, EncScratch& scratch, i
         warps = std::min(std::max(warps, 1), P.geo.max_warps);
         if (const char* ev = getenv("LZB_ENC_WARPS")) warps = std::min(std::max(atoi(ev), 1), P.geo.max_warps);  // tuning knob
         const int grid = (int)std::min<uint32_t>((wb + (uint32_t)warps - 1) / (uint32_t)warps, (uint32_t)num_sms);
+        // More blocks than parser slots: a block that starts late must not be a slow one, or the wave
+        // ends on it with the GPU idle.  The parser's cost grows with the bytes to code and with the
+        // match pairs it has to price, so blocks are handed out by decreasing (length + pair words).
+        pa.order = nullptr;
+        if (wb > (uint32_t)(grid * warps) && getenv("LZB_ENC_FIFO") == nullptr) {
+            std::vector<uint32_t> used(wb), order(wb);
+            std::vector<uint64_t> len(wb);
+            e = cudaMemcpyAsync(used.data(), w.pair_used, (size_t)wb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return e;
+            e = cudaMemcpyAsync(len.data(), w.in_len, (size_t)wb * sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return e;
+            for (uint32_t i = 0; i < wb; i++) order[i] = i;
+            std::stable_sort(order.begin(), order.end(),
+                             [&](uint32_t x, uint32_t y) { return len[x] + used[x] > len[y] + used[y]; });
+            e = cudaMemcpyAsync(order_dev, order.data(), (size_t)wb * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(st);  // `order` is pageable host memory that dies with this scope
+            if (e != cudaSuccess) return e;
+            pa.order = order_dev;
+        }
         e = launch_parse(pa, grid, warps, st);
         if (e != cudaSuccess) return e;
         *nl += 1;
@@ -233,125 +283,12 @@ cudaError_t run_waves(const EncodeArgs& a, const Plan& P, EncScratch& scratch, i
     return cudaSuccess;
 }
 
-// Batches with more blocks than resident parser slots: groups of `group` blocks go round-robin
-// over `lanes` lanes, each lane a CUDA stream with its own scratch set running
-// match finder -> parse for its groups in order.  The parser runs one warp per CTA here, so the
-// hardware block scheduler keeps every SM's parser slots filled from whichever lanes have
-// parse CTAs pending, and the match finder of later groups runs in the issue slots the
-// latency-bound parsers leave idle.  No host synchronisation until the end: a group that ran out
-// of pair slots is skipped by its parse kernel (flag checked on the device) and redone afterwards.
-cudaError_t run_pipelined(const EncodeArgs& a, const Plan& P, EncScratch& scratch, int num_sms, cudaStream_t st, size_t budget,
-                          uint32_t group, uint32_t lanes, uint32_t pair_mul, int* nl) {
-    const uint32_t pair_cap = pair_cap_for(pair_mul, a.max_in_len);
-    const uint32_t n_groups = (a.n + group - 1) / group;
-    const size_t set_bytes =
-        (carve(nullptr, group, P.np, P.hash_stride, pair_cap, group, group * P.lit_per_slot, nullptr, nullptr, nullptr) + 255) & ~size_t(255);
-    const size_t head_bytes = ((size_t)n_groups * sizeof(uint32_t) + 255) & ~size_t(255);  // one overflow flag per group
-    cudaError_t e = grow(scratch, head_bytes + (size_t)lanes * set_bytes, st);
-    if (e != cudaSuccess) return e;
-    e = scratch.ensure_lanes(lanes);
-    if (e != cudaSuccess) return e;
-    uint32_t* d_ovf = reinterpret_cast<uint32_t*>(scratch.p);
-    uint8_t* sets = (uint8_t*)scratch.p + head_bytes;
-
-    cudaEvent_t tev[2] = {nullptr, nullptr};
-    if (P.timing) {
-        for (auto& x : tev) cudaEventCreate(&x);
-        cudaEventRecord(tev[0], st);
-    }
-    e = cudaMemsetAsync(d_ovf, 0, head_bytes, st);
-    if (e != cudaSuccess) return e;
-    e = cudaEventRecord(scratch.fork, st);
-    if (e != cudaSuccess) return e;
-    for (uint32_t l = 0; l < lanes; l++) {
-        e = cudaStreamWaitEvent(scratch.lanes[l], scratch.fork, 0);
-        if (e != cudaSuccess) return e;
-    }
-    for (uint32_t g = 0; g < n_groups; g++) {
-        const uint32_t l = g % lanes, first = g * group, gb = std::min(group, a.n - first);
-        cudaStream_t ls = scratch.lanes[l];
-        uint8_t* base = sets + (size_t)l * set_bytes;
-        MfWave w;
-        ParseArgs pa;
-        size_t zero_len = 0;
-        bind_wave(a, P, base, first, gb, pair_cap, group, &w, &pa, &zero_len);
-        w.overflow = d_ovf + g;
-        e = cudaMemsetAsync(base, 0, zero_len, ls);
-        if (e != cudaSuccess) return e;
-        e = launch_mf(w, (uint32_t)a.max_in_len, num_sms, ls);
-        if (e != cudaSuccess) return e;
-        pa.mf = w;
-        e = launch_parse(pa, (int)gb, 1, ls);
-        if (e != cudaSuccess) return e;
-        *nl += a.max_in_len ? 4 : 2;
-    }
-    for (uint32_t l = 0; l < lanes; l++) {
-        e = cudaEventRecord(scratch.joins[l], scratch.lanes[l]);
-        if (e != cudaSuccess) return e;
-        e = cudaStreamWaitEvent(st, scratch.joins[l], 0);
-        if (e != cudaSuccess) return e;
-    }
-    std::vector<uint32_t> ovf(n_groups, 0);
-    e = cudaMemcpyAsync(ovf.data(), d_ovf, (size_t)n_groups * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return e;
-    if (P.timing) cudaEventRecord(tev[1], st);
-    e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return e;
-    if (P.timing) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, tev[0], tev[1]);
-        fprintf(stderr, "lzb_enc pipeline: %u blocks (max %llu B) in %u groups of %u over %u lanes, %.1f ms\n", a.n,
-                (unsigned long long)a.max_in_len, n_groups, group, lanes, ms);
-        for (auto& x : tev) cudaEventDestroy(x);
-    }
-    for (uint32_t g = 0; g < n_groups; g++) {  // rare: redo the groups whose match lists did not fit
-        if (!ovf[g]) continue;
-        if (pair_mul >= 512) return cudaErrorMemoryAllocation;
-        const uint32_t first = g * group, gb = std::min(group, a.n - first);
-        e = run_waves(a, P, scratch, num_sms, st, budget, first, gb, pair_mul * 2, nl, nullptr);
-        if (e != cudaSuccess) return e;
-        e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) return e;
-    }
-    return cudaSuccess;
-}
-
-int env_int(const char* name, int fallback) {
-    const char* ev = getenv(name);
-    return ev ? atoi(ev) : fallback;
-}
-
 }  // namespace
 
 void EncScratch::release() {
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
-    for (cudaStream_t s : lanes) cudaStreamDestroy(s);
-    for (cudaEvent_t ev : joins) cudaEventDestroy(ev);
-    if (fork) cudaEventDestroy(fork);
-    lanes.clear();
-    joins.clear();
-    fork = nullptr;
-}
-
-cudaError_t EncScratch::ensure_lanes(uint32_t count) {
-    cudaError_t e;
-    if (!fork) {
-        e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
-        if (e != cudaSuccess) return e;
-    }
-    while (lanes.size() < count) {
-        cudaStream_t s = nullptr;
-        e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-        if (e != cudaSuccess) return e;
-        lanes.push_back(s);
-        cudaEvent_t ev = nullptr;
-        e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-        if (e != cudaSuccess) return e;
-        joins.push_back(ev);
-    }
-    return cudaSuccess;
 }
 
 cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cudaStream_t st, int* launches, MfTrace* mf_only) {
@@ -380,24 +317,6 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
     uint32_t pair_mul = 6;  // pair slots per input byte (text needs ~4.4); doubled when a wave overflows
     if (const char* ev = getenv("LZB_PAIR_MUL")) pair_mul = (uint32_t)std::max(atoi(ev), 1);  // test knob for the retry path
 
-    // More blocks than resident parser slots: pipeline groups over lanes (run_pipelined).
-    // LZB_ENC_PIPE=0/1 forces the choice, LZB_ENC_GROUP / LZB_ENC_LANES set the shape (test knobs).
-    const size_t resident = (size_t)num_sms * P.geo.max_warps;
-    const int pipe = env_int("LZB_ENC_PIPE", -1);
-    if (!mf_only && pipe != 0 && (pipe == 1 || a.n > resident)) {
-        const uint32_t lanes = (uint32_t)std::min(std::max(env_int("LZB_ENC_LANES", 6), 1), 16);
-        const uint32_t pair_cap = pair_cap_for(pair_mul, a.max_in_len);
-        const size_t per_block =
-            carve(nullptr, 64, P.np, P.hash_stride, pair_cap, 64, 64 * P.lit_per_slot, nullptr, nullptr, nullptr) / 64 + 1;
-        uint32_t group = (uint32_t)std::min<size_t>(2 * (size_t)num_sms, budget / lanes / per_block);
-        if (const char* ev = getenv("LZB_ENC_GROUP")) group = (uint32_t)std::max(atoi(ev), 1);
-        if (group >= 8 || pipe == 1) {
-            group = std::max(group, 1u);
-            e = run_pipelined(a, P, scratch, num_sms, st, budget, group, std::min(lanes, (a.n + group - 1) / group), pair_mul, &nl);
-            if (launches) *launches = nl;
-            return e;
-        }
-    }
     e = run_waves(a, P, scratch, num_sms, st, budget, 0, a.n, pair_mul, &nl, mf_only);
     if (launches) *launches = nl;
     return e;

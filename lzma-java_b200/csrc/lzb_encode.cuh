@@ -68,6 +68,7 @@ struct ParseArgs {
     const uint64_t* out_cap;
     uint64_t* out_len;
     uint32_t* ticket;        // zeroed
+    const uint32_t* order;   // ticket -> block of the wave, or nullptr for the identity
     void* opt_scratch;       // [grid * warps][4096] packed _optimum nodes
     uint16_t* lit_scratch;   // [grid * warps][0x300 << (lc+lp)] when the literal model does not fit shared memory
     int32_t dict_size, dist_table_size;

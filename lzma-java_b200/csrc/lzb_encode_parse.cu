@@ -1298,9 +1298,6 @@ __device__ __forceinline__ void Enc::run() {
 __global__ void __launch_bounds__(kEncMaxWarps * 32, 1) lzb_parse_kernel(ParseArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CtaTables* tables = reinterpret_cast<CtaTables*>(smem_raw);
-    // the pipelined path launches without asking the host first: lists that did not fit their
-    // pair slots are incomplete, the host redoes such a group with more room
-    if (*a.mf.overflow) return;
     init_cta_tables(tables);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;
@@ -1317,6 +1314,7 @@ __global__ void __launch_bounds__(kEncMaxWarps * 32, 1) lzb_parse_kernel(ParseAr
         if (lane == 0) b = atomicAdd(a.ticket, 1u);
         b = __shfl_sync(kFull, b, 0);
         if (b >= a.mf.n_blocks) break;
+        if (a.order) b = a.order[b];
         const uint32_t n = (uint32_t)a.mf.in_len[b];
         uint8_t* out = a.out + a.out_off[b];
         uint64_t cap = a.out_cap[b];
@@ -1410,9 +1408,6 @@ size_t parse_opt_bytes_per_slot() { return sizeof(OptNode) * (size_t)kNumOpts; }
 cudaError_t launch_parse(const ParseArgs& a, int grid, int warps, cudaStream_t st) {
     const size_t smem = sizeof(CtaTables) + (size_t)warps * a.slice_bytes;
     cudaError_t e = cudaFuncSetAttribute(lzb_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    if (e != cudaSuccess) return e;
-    // small CTAs (one warp each on the pipelined path) must still fill the SM's shared memory
-    e = cudaFuncSetAttribute(lzb_parse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     lzb_parse_kernel<<<grid, warps * 32, smem, st>>>(a);
     return cudaGetLastError();

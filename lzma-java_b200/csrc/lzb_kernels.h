@@ -5,7 +5,6 @@
 #include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
-#include <vector>
 
 #define LZB_KERNEL_HEADER 13
 #define LZB_KERNEL_E_CAPACITY (-4)
@@ -73,15 +72,10 @@ struct EncodeArgs {
     bool eos, with_header;
 };
 
-// device resources owned by an encoder handle: grow-only scratch, and the lane streams of the
-// pipelined path (lzb_encode.cu, run_pipelined) with their fork / join events
+// device scratch owned by an encoder handle (grow-only)
 struct EncScratch {
     void* p = nullptr;
     size_t cap = 0;
-    std::vector<cudaStream_t> lanes;
-    std::vector<cudaEvent_t> joins;
-    cudaEvent_t fork = nullptr;
-    cudaError_t ensure_lanes(uint32_t count);
     void release();
 };
 

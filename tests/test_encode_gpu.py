@@ -189,21 +189,17 @@ def test_encode_many_tiny_blocks_and_pair_overflow_retry(lzb, oracle, corpus, mo
     _check(lzb, oracle, BASE, text)
 
 
-def test_encode_pipelined_groups_over_lanes(lzb, oracle, corpus, monkeypatch):
-    """Batches with more blocks than resident parser slots flow through lanes in groups (lzb_encode.cu,
-    run_pipelined); forced here on a small batch: ragged last group, more groups than lanes, every block == oracle."""
-    monkeypatch.setenv("LZB_ENC_PIPE", "1")
-    monkeypatch.setenv("LZB_ENC_GROUP", "3")
-    monkeypatch.setenv("LZB_ENC_LANES", "2")
-    blocks = [corpus.generate(3000 + 977 * i, 1, i % 4, 29, i).tobytes() for i in range(17)] + [b"", b"z"]
-    _check(lzb, oracle, BASE, blocks)
-    p = dict(BASE)
-    p.update(fb=64, lc=4, lp=4, pb=3)  # literal coder in global memory: one slot per CTA of the group
-    _check(lzb, oracle, p, blocks[:7])
-    # groups whose match lists overflow their pair slots are skipped on the device and redone afterwards
-    monkeypatch.setenv("LZB_PAIR_MUL", "1")
-    text = [corpus.generate(20000, 1, k % 2, 30, k).tobytes() for k in range(8)]
-    _check(lzb, oracle, BASE, text)
+def test_encode_more_blocks_than_parser_slots(lzb, oracle, corpus, monkeypatch):
+    """A wave with more blocks than resident parser slots hands its blocks out longest-expected-first
+    (lzb_encode.cu, run_waves); one parser slot per SM forces that on a small batch.  Placement of the
+    outputs must not depend on the order: every block == oracle."""
+    monkeypatch.setenv("LZB_ENC_WARPS", "1")
+    blocks = [corpus.generate(500 + 37 * (i % 50), 1, i % 4, 29, i).tobytes() for i in range(400)] + [b"", b"z"]
+    got = _gpu_streams(lzb, BASE, blocks)
+    for i, b in enumerate(blocks):
+        assert got[i] == oracle.encode(b, oracle.props(**BASE), alone=True), i
+    monkeypatch.setenv("LZB_ENC_FIFO", "1")  # the plain ticket order gives the same bytes
+    assert _gpu_streams(lzb, BASE, blocks) == got
 
 
 @pytest.mark.parametrize("kw", [{}, {"fb": 64}, {"fb": 273, "dict_size": 1 << 23}, {"mf": 0}, {"dict_size": 4096}, {"dict_size": 1}])

@@ -42,6 +42,19 @@ def run(n, size, cls, fb, dict_size, iters=1):
 
 
 if __name__ == "__main__":
+    # spec: n,size,cls,fb,dict[,iters][;ENV=VALUE...]   (environment knobs apply to that spec only)
     for spec in sys.argv[1:]:
-        n, size, cls, fb, d = (int(x) for x in spec.split(","))
-        run(n, size, cls, fb, d)
+        parts = spec.split(";")
+        saved = {}
+        for kv in parts[1:]:
+            k, v = kv.split("=")
+            saved[k] = os.environ.get(k)
+            os.environ[k] = v
+        nums = [int(x) for x in parts[0].split(",")]
+        print("SPEC", spec, flush=True)
+        run(*nums[:5], iters=nums[5] if len(nums) > 5 else 1)
+        for k, v in saved.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
