@@ -13,7 +13,7 @@ of the batch decoder over the whole batch.
   cpu_baseline  the CPU oracle (a C port of the reference; no JVM exists on the
             box) decoding the same streams on all host cores
   encode    extra object: BASELINE.json configs[2] (1 MiB blocks, dict 1 MiB,
-            fb 64, mixed corpus) measured the same way
+            fb 64, mixed corpus; 2048 blocks = 2 GiB per GPU) measured the same way
 The compressed streams are produced by this repo's GPU encoder (bit-identical
 to the reference encoder, tests/test_encode_gpu.py) during untimed set-up, and
 the decoded bytes are compared with the corpus inside the run.
@@ -401,7 +401,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=4096, help="decode streams per GPU (configs[1]: 4096)")
-    ap.add_argument("--enc-blocks", type=int, default=1024, help="1 MiB blocks per GPU for the encode extra")
+    ap.add_argument("--enc-blocks", type=int, default=2048, help="1 MiB blocks per GPU for the encode extra (configs[2] fixes the block size, not the count)")
     ap.add_argument("--enc-steps", type=int, default=2)
     ap.add_argument("--enc-cpu-blocks", type=int, default=128)
     ap.add_argument("--no-encode", action="store_true")

@@ -311,8 +311,8 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
     size_t free_b = 0, total_b = 0;
     e = cudaMemGetInfo(&free_b, &total_b);
     if (e != cudaSuccess) return e;
-    // the scratch may take up to 3/4 of what is free (plus what this handle already holds)
-    const size_t budget = std::max<size_t>((free_b + scratch.cap) / 4 * 3, size_t(256) << 20);
+    // the scratch may take up to 7/8 of what is free (plus what this handle already holds)
+    const size_t budget = std::max<size_t>((free_b + scratch.cap) / 8 * 7, size_t(256) << 20);
 
     uint32_t pair_mul = 6;  // pair slots per input byte (text needs ~4.4); doubled when a wave overflows
     if (const char* ev = getenv("LZB_PAIR_MUL")) pair_mul = (uint32_t)std::max(atoi(ev), 1);  // test knob for the retry path
