@@ -242,8 +242,11 @@ cudaError_t run_waves(const EncodeArgs& a, const Plan& P, EncScratch& scratch, i
         // More blocks than parser slots: a block that starts late must not be a slow one, or the wave
         // ends on it with the GPU idle.  The parser's cost grows with the bytes to code and with the
         // match pairs it has to price, so blocks are handed out by decreasing (length + pair words).
+        // With fewer blocks the same order still pays: the warps of a CTA draw neighbouring tickets, so an
+        // SM's streams are alike and run the same parts of the kernel, which its instruction cache likes
+        // (profiles/r01_parse_kernel_mixed_w8_w2_ncu.txt).
         pa.order = nullptr;
-        if (wb > (uint32_t)(grid * warps) && getenv("LZB_ENC_FIFO") == nullptr) {
+        if (wb > (uint32_t)num_sms && getenv("LZB_ENC_FIFO") == nullptr) {
             std::vector<uint32_t> used(wb), order(wb);
             std::vector<uint64_t> len(wb);
             e = cudaMemcpyAsync(used.data(), w.pair_used, (size_t)wb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
