@@ -3,9 +3,9 @@
 // Replaces Encoder.Code (LZMA/Encoder.java:1064-1077) for a batch of
 // independent blocks.  Per wave of blocks:  memset(heads, next, counters) ->
 // lzb_mf_link_kernel -> lzb_mf_tree_kernel -> lzb_mf_long_kernel -> lzb_parse_kernel.
-// A wave holds as many blocks as the memory budget allows; when it holds more blocks than the
-// parser has resident slots, the parser takes them longest-expected-first (most match pairs
-// first), so the wave does not end on a late-started slow block.
+// A wave holds as many blocks as the memory budget allows.  The parser takes a wave's blocks
+// longest-expected-first (most match pairs first): a wave with more blocks than resident parser
+// slots then does not end on a late-started slow block, and the streams that share an SM are alike.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
