@@ -246,13 +246,22 @@ class Decoder:
         return ok
 
     def code_bytes(self, payload, out_size, out_cap=None):
+        """One payload -> (ok, bytes).  With out_size < 0 (decode until the end marker,
+        Decoder.java:219,277-282) the output size is unknown: start from a guess and, like the Java
+        binding, grow the buffer and decode again while the library reports LZB_E_CAPACITY."""
         a = _u8(payload)
+        grow = out_cap is None and out_size < 0
         if out_cap is None:
-            out_cap = (out_size if out_size >= 0 else 64 * a.size + 4096) + 273
-        out = np.empty(max(out_cap, 1), dtype=np.uint8)
-        w = C.c_uint64(0)
-        rc = _check(lib().lzb_dec_code(self._h, a.ctypes.data, a.size, out.ctypes.data, out_cap, out_size, C.byref(w)))
-        return rc == 1, out[: w.value].tobytes()
+            out_cap = (out_size if out_size >= 0 else 8 * a.size + 4096) + 273
+        while True:
+            out = np.empty(max(out_cap, 1), dtype=np.uint8)
+            w = C.c_uint64(0)
+            rc = lib().lzb_dec_code(self._h, a.ctypes.data, a.size, out.ctypes.data, out_cap, out_size, C.byref(w))
+            if rc == LZB_E_CAPACITY and grow and out_cap < (1 << 32) - (1 << 20):
+                out_cap = min(out_cap * 4, (1 << 32) - (1 << 20))
+                continue
+            _check(rc)
+            return rc == 1, out[: w.value].tobytes()
 
     def code_batch(self, in_arr, in_off, in_len, out_off, out_cap):
         """n LzmaAlone streams from host memory -> (out, out_len, status)."""

@@ -69,6 +69,10 @@ struct lzb_dec {
     PinBuf h_meta, h_progress;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-buffer batches overlap transfers with the kernels
     cudaStream_t kstream[4] = {nullptr, nullptr, nullptr, nullptr};  // ... whose chunks share the SMs
+    // developer / test hooks, read ONCE when the handle is created (DESIGN.md "test hooks")
+    int env_mode = -1;    // LZB_DEC_MODE: 0 = all shared, 1 = hybrid
+    int env_chunks = 0;   // LZB_DEC_CHUNKS: 1..16
+    int env_marks = 0;    // LZB_DEC_MARKS: 1..32
 };
 
 namespace {
@@ -86,15 +90,13 @@ void header_scan(const uint8_t* stream, uint64_t len, uint32_t* max_lclp1, uint3
 // Where the models of a launch live (lzb_kernels.h, DecMode).  `resident` = streams that will be
 // in flight together: the hybrid mode trades a slower literal-after-match for twice the
 // streams per SM, which only pays when the all-shared mode could not hold them at once.
-int pick_dec_mode(uint32_t max_lclp1, uint32_t max_pb1, uint64_t resident, int num_sms) {
+int pick_dec_mode(uint32_t max_lclp1, uint32_t max_pb1, uint64_t resident, int num_sms, int forced) {
     if (max_lclp1 > 4) return lzb::kDecGlobal;
     if (max_lclp1 == 0) return lzb::kDecSmem;  // no well-formed header: every stream returns 0 at once
     const lzb::ModelLayout L = lzb::make_layout((int)max_lclp1 - 1, 0, (int)max_pb1 - 1);
     if ((size_t)(L.n_fixed + L.n_literal) * 2 > lzb::kDecSliceBytes) return lzb::kDecHybrid;  // lc + lp = 3 with pb = 4
-    if (const char* e = getenv("LZB_DEC_MODE")) {  // test hook: 0 = all shared, 1 = hybrid
-        if (e[0] == '0') return lzb::kDecSmem;
-        if (e[0] == '1') return lzb::kDecHybrid;
-    }
+    if (forced == 0) return lzb::kDecSmem;  // test hook
+    if (forced == 1) return lzb::kDecHybrid;
     return resident > (uint64_t)num_sms * lzb::kDecMaxWarps ? lzb::kDecHybrid : lzb::kDecSmem;
 }
 
@@ -169,6 +171,9 @@ lzb_dec* lzb_dec_create(int device) {
         delete d;
         return nullptr;
     }
+    if (const char* e = getenv("LZB_DEC_MODE")) d->env_mode = e[0] == '0' ? 0 : e[0] == '1' ? 1 : -1;
+    if (const char* e = getenv("LZB_DEC_CHUNKS")) d->env_chunks = atoi(e);
+    if (const char* e = getenv("LZB_DEC_MARKS")) d->env_marks = atoi(e);
     return d;
 }
 
@@ -225,7 +230,7 @@ int lzb_dec_code_batch_device(lzb_dec* d, const uint8_t* d_in, const uint64_t* d
     CUDA_TRY(cudaStreamSynchronize(st));
 
     return dec_enqueue(d, d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_cap, d_out_len, d_status, scan[0],
-                       pick_dec_mode(scan[0], scan[1], n, d->num_sms), ctrl, st);
+                       pick_dec_mode(scan[0], scan[1], n, d->num_sms, d->env_mode), ctrl, st);
 }
 
 int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len, uint32_t n,
@@ -273,7 +278,7 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
     // (b) Any other layout: chunks of about 7 streams per SM, each with its own input copy, kernel
     //     launch and output copy; the kernels go round-robin over up to four streams so that four
     //     chunks share the SMs (4 x 7 warps = the residency of one big launch).
-    const int mode = pick_dec_mode(max_lclp1, max_pb1, n, d->num_sms);
+    const int mode = pick_dec_mode(max_lclp1, max_pb1, n, d->num_sms, d->env_mode);
     const uint32_t n_k = mode == lzb::kDecGlobal ? 1u : 4u;  // kDecGlobal: scratch can be GBs, one launch at a time
     for (uint32_t k = 0; k < n_k; k++)
         if (!d->kstream[k]) CUDA_TRY(cudaStreamCreateWithFlags(&d->kstream[k], cudaStreamNonBlocking));
@@ -286,10 +291,7 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
         for (uint32_t i = 1; i < n && whole; i++) whole = out_cap[i] == out_cap[0] && out_off[i] == out_off[0] + (uint64_t)i * pitch;
         if (whole) n_chunks = 1;
     }
-    if (const char* e = getenv("LZB_DEC_CHUNKS")) {  // test hook
-        const int v = atoi(e);
-        if (v >= 1 && v <= 16 && (uint32_t)v <= n) n_chunks = (uint32_t)v;
-    }
+    if (d->env_chunks >= 1 && d->env_chunks <= 16 && (uint32_t)d->env_chunks <= n) n_chunks = (uint32_t)d->env_chunks;  // test hook
     std::vector<uint32_t> first(n_chunks + 1);
     std::vector<Span> cin(n_chunks), cout(n_chunks);
     for (uint32_t c = 0; c <= n_chunks; c++) first[c] = (uint32_t)((uint64_t)n * c / n_chunks);
@@ -313,16 +315,14 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
     // Other layouts are copied chunk by chunk after their kernel.
     constexpr uint32_t kMaxMarks = 32;
     uint32_t kMarks = 8;
-    if (const char* e = getenv("LZB_DEC_MARKS")) {  // test hook
-        const int v = atoi(e);
-        if (v >= 1 && v <= (int)kMaxMarks) kMarks = (uint32_t)v;
-    }
+    if (d->env_marks >= 1 && d->env_marks <= (int)kMaxMarks) kMarks = (uint32_t)d->env_marks;  // test hook
     struct Rows {
         bool on = false;
         uint64_t pitch = 0, cap = 0;
         uint32_t step = 0, marks = 0, issued = 0;
     };
     std::vector<Rows> rows(n_chunks);
+    std::vector<char> span_copy(n_chunks, 1);
     uint32_t pending_marks = 0;
     for (uint32_t c = 0; c < n_chunks && ordered; c++) {
         const uint32_t s0 = first[c], cnt = first[c + 1] - s0;
@@ -381,7 +381,12 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
         if (rc != LZB_OK) break;
         cudaEventRecord(ev_k[c], ks);
         cudaStreamWaitEvent(st, ev_k[c], 0);  // the out_len / status read-back below follows every kernel
-        if (!rows[c].on && cout[c].hi > cout[c].lo) {
+        // A chunk whose regions tile its span may leave in one copy (bytes past out_len[i] inside a
+        // stream's own [out_off, out_off + out_cap) are the stream's to clobber).  With gaps between
+        // the regions the caller may keep other data there: such chunks are fetched stream by stream
+        // once the lengths are known (below).
+        span_copy[c] = cout[c].sum == cout[c].hi - cout[c].lo;
+        if (!rows[c].on && span_copy[c] && cout[c].hi > cout[c].lo) {
             cudaStreamWaitEvent(d->copy_out, ev_k[c], 0);
             err = cudaMemcpyAsync(out + cout[c].lo, d_out + (cout[c].lo - so.lo), cout[c].hi - cout[c].lo, cudaMemcpyDeviceToHost,
                                   d->copy_out);
@@ -420,6 +425,15 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
         err = cudaMemcpyAsync(hm + 4 * (size_t)n, dm + 4 * (size_t)n, (size_t)n * (sizeof(uint64_t) + sizeof(int32_t)),
                               cudaMemcpyDeviceToHost, st);
     cudaError_t e1 = cudaStreamSynchronize(st);
+    if (rc == LZB_OK && err == cudaSuccess && e1 == cudaSuccess) {
+        const uint64_t* lens = hm + 4 * (size_t)n;
+        for (uint32_t c = 0; c < n_events && err == cudaSuccess; c++) {
+            if (rows[c].on || span_copy[c]) continue;
+            for (uint32_t i = first[c]; i < first[c + 1] && err == cudaSuccess; i++)
+                if (lens[i])
+                    err = cudaMemcpyAsync(out + out_off[i], d_out + (out_off[i] - so.lo), lens[i], cudaMemcpyDeviceToHost, d->copy_out);
+        }
+    }
     const cudaError_t e2 = cudaStreamSynchronize(d->copy_out), e3 = cudaStreamSynchronize(d->copy_in);
     for (uint32_t k = 0; k < n_k; k++) {
         const cudaError_t ek = cudaStreamSynchronize(d->kstream[k]);

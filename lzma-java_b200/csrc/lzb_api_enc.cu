@@ -2,6 +2,7 @@
 #include "../../include/lzma_b200.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -25,6 +26,9 @@ struct lzb_enc {
     lzb::EncScratch scratch;
     DevBuf d_in, d_out, d_meta;
     PinBuf h_meta;
+    // developer / test hooks (DESIGN.md "test hooks"), read ONCE when the handle is created
+    int32_t tune_warps = 0, tune_pair_mul = 0;
+    bool tune_fifo = false, tune_timing = false;
 };
 
 extern "C" {
@@ -40,6 +44,10 @@ lzb_enc* lzb_enc_create(int device) {
         delete e;
         return nullptr;
     }
+    if (const char* v = getenv("LZB_ENC_WARPS")) e->tune_warps = atoi(v) > 0 ? atoi(v) : 0;
+    if (const char* v = getenv("LZB_PAIR_MUL")) e->tune_pair_mul = atoi(v) > 0 ? atoi(v) : 0;
+    e->tune_fifo = getenv("LZB_ENC_FIFO") != nullptr;
+    e->tune_timing = getenv("LZB_ENC_TIMING") != nullptr;
     return e;
 }
 
@@ -129,9 +137,14 @@ int lzb_enc_code_batch_device(lzb_enc* e, const uint8_t* d_in, const uint64_t* d
     a.pb = e->pb;
     a.eos = e->eos;
     a.with_header = with_header13 != 0;
+    a.tune_warps = e->tune_warps;
+    a.tune_pair_mul = e->tune_pair_mul;
+    a.tune_fifo = e->tune_fifo;
+    a.tune_timing = e->tune_timing;
     int launches = 0;
     cudaError_t err = lzb::run_encode(a, e->scratch, e->num_sms, st, &launches);
     add_launches(launches);
+    if (err == cudaErrorInvalidValue) return fail(LZB_E_ARG, "encode: a block is longer than max_in_len = %llu", (unsigned long long)max_in_len);
     if (err != cudaSuccess)
         return fail(err == cudaErrorMemoryAllocation ? LZB_E_NOMEM : LZB_E_CUDA, "encode: %s", cudaGetErrorString(err));
     return LZB_OK;

@@ -215,6 +215,7 @@ cudaError_t run_waves(const EncodeArgs& a, const Plan& P, EncScratch& scratch, i
         e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return e;
         if (P.timing) cudaEventRecord(tev[1], st);
+        if (overflow >= 2) return cudaErrorInvalidValue;  // a block longer than the declared max_in_len
         if (overflow) {
             if (P.timing)
                 for (auto& x : tev) cudaEventDestroy(x);
@@ -237,7 +238,7 @@ cudaError_t run_waves(const EncodeArgs& a, const Plan& P, EncScratch& scratch, i
         pa.mf = w;
         int warps = (int)((wb + (uint32_t)num_sms - 1) / (uint32_t)num_sms);
         warps = std::min(std::max(warps, 1), P.geo.max_warps);
-        if (const char* ev = getenv("LZB_ENC_WARPS")) warps = std::min(std::max(atoi(ev), 1), P.geo.max_warps);  // tuning knob
+        if (a.tune_warps > 0) warps = std::min((int)a.tune_warps, P.geo.max_warps);  // tuning knob
         const int grid = (int)std::min<uint32_t>((wb + (uint32_t)warps - 1) / (uint32_t)warps, (uint32_t)num_sms);
         // More blocks than parser slots: a block that starts late must not be a slow one, or the wave
         // ends on it with the GPU idle.  The parser's cost grows with the bytes to code and with the
@@ -246,7 +247,7 @@ cudaError_t run_waves(const EncodeArgs& a, const Plan& P, EncScratch& scratch, i
         // SM's streams are alike and run the same parts of the kernel, which its instruction cache likes
         // (profiles/r01_parse_kernel_mixed_w8_w2_ncu.txt).
         pa.order = nullptr;
-        if (wb > (uint32_t)num_sms && getenv("LZB_ENC_FIFO") == nullptr) {
+        if (wb > (uint32_t)num_sms && !a.tune_fifo) {
             std::vector<uint32_t> used(wb), order(wb);
             std::vector<uint64_t> len(wb);
             e = cudaMemcpyAsync(used.data(), w.pair_used, (size_t)wb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
@@ -309,7 +310,7 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
     while ((uint32_t)a.dict_size > (1u << P.dic_log)) P.dic_log++;  // Encoder.java:1141-1144
     P.geo = parse_geometry(a.lc, a.lp, a.pb, a.fb);
     P.lit_per_slot = P.geo.lit_in_smem ? 0 : ((size_t)0x300 << (a.lc + a.lp));
-    P.timing = getenv("LZB_ENC_TIMING") != nullptr;
+    P.timing = a.tune_timing;
 
     size_t free_b = 0, total_b = 0;
     e = cudaMemGetInfo(&free_b, &total_b);
@@ -318,7 +319,7 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
     const size_t budget = std::max<size_t>((free_b + scratch.cap) / 8 * 7, size_t(256) << 20);
 
     uint32_t pair_mul = 6;  // pair slots per input byte (text needs ~4.4); doubled when a wave overflows
-    if (const char* ev = getenv("LZB_PAIR_MUL")) pair_mul = (uint32_t)std::max(atoi(ev), 1);  // test knob for the retry path
+    if (a.tune_pair_mul > 0) pair_mul = (uint32_t)a.tune_pair_mul;  // test knob for the retry path
 
     e = run_waves(a, P, scratch, num_sms, st, budget, 0, a.n, pair_mul, &nl, mf_only);
     if (launches) *launches = nl;

@@ -74,6 +74,10 @@ __global__ void __launch_bounds__(128) lzb_mf_link_kernel(MfWave w) {
     const int lane = threadIdx.x & 31;
     if (b >= w.n_blocks) return;
     const uint8_t* data = w.in + w.in_off[b];
+    if (w.in_len[b] > (uint64_t)w.np - 1) {  // longer than the caller's max_in_len: the scratch slices would overflow
+        if (lane == 0) atomicMax(w.overflow, 2u);
+        return;
+    }
     const uint32_t n = (uint32_t)w.in_len[b];
     uint32_t* heads = w.heads + (size_t)b * w.hash_stride;
     uint32_t* next = w.next + (size_t)b * w.np;
@@ -204,7 +208,7 @@ __device__ __forceinline__ void tree_store_list(const MfWave& w, const TreeBlock
                 t.pairs2_out[off + 1 + i] = (uint16_t)k;
             }
         } else {
-            *w.overflow = 1;
+            atomicMax(w.overflow, 1u);
         }
     }
     t.idx[pos1] = where;
@@ -214,6 +218,7 @@ __device__ __forceinline__ void tree_store_list(const MfWave& w, const TreeBlock
 // chain to lzb_mf_long_kernel, which pipelines the insertions of one chain across a warp.
 __global__ void __launch_bounds__(256) lzb_mf_tree_kernel(MfWave w) {
     const uint32_t b = blockIdx.y;
+    if (w.in_len[b] > (uint64_t)w.np - 1) return;  // flagged by the link kernel
     const uint32_t n = (uint32_t)w.in_len[b];
     const uint32_t p0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (p0 >= n) return;

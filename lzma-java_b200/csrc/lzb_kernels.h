@@ -70,6 +70,11 @@ struct EncodeArgs {
     bool bt4;
     int32_t lc, lp, pb;
     bool eos, with_header;
+    // developer / test hooks, read once when the handle is created (lzb_enc_create)
+    int32_t tune_warps = 0;      // LZB_ENC_WARPS: parser streams per SM (0 = automatic)
+    int32_t tune_pair_mul = 0;   // LZB_PAIR_MUL: initial match-pair budget in slots per input byte (0 = default)
+    bool tune_fifo = false;      // LZB_ENC_FIFO: plain block order inside a wave
+    bool tune_timing = false;    // LZB_ENC_TIMING: phase times of every wave on stderr
 };
 
 // device scratch owned by an encoder handle (grow-only)

@@ -210,3 +210,50 @@ def test_decode_progressive_readback(lzb, oracle, corpus, chunks, monkeypatch):
     for i in range(n):
         a, b = int(ooff[i]), int(ooff[i]) + int(out_len[i])
         assert np.array_equal(out[a:b], ref_out[a:b]), i
+
+
+def test_decode_alone_end_marker_grows_the_output(lzb, oracle):
+    """An end-marker stream says nothing about its size; one that expands far beyond the first guess
+    (here 100 000 zeros in ~40 bytes) must still decode: the mirror grows the buffer and decodes again
+    on LZB_E_CAPACITY, as java/.../Decoder.java does (Decoder.java:219,277-282: outSize < 0)."""
+    data = b"\0" * 100000 + b"tail"
+    p = dict(BASE)
+    p["eos"] = True
+    s = oracle.encode(data, oracle.props(**p), alone=True)
+    assert len(s) < 200
+    ok, back = lzb.decode_alone(s)
+    assert ok and back == data
+    s2 = lzb.encode_alone(data, eos=True)
+    ok, back = lzb.decode_alone(s2)
+    assert ok and back == data
+
+
+def test_decode_batch_leaves_gaps_between_outputs_alone(lzb, oracle, corpus):
+    """include/lzma_b200.h promises writes only inside out[out_off[i] .. out_off[i] + out_cap[i]): host
+    bytes between the regions (ragged capacities, so not the row-shaped fast path) keep their values."""
+    n = 700
+    sizes = [3000 + 17 * (i % 40) for i in range(n)]
+    blocks = [corpus.generate(sz, 1, i % 4, 31, i).tobytes() for i, sz in enumerate(sizes)]
+    streams = [oracle.encode(b, oracle.props(**BASE), alone=True) for b in blocks]
+    arr, off, ln = _pack(streams)
+    cap = np.array([sz + 273 for sz in sizes], dtype=np.uint64)
+    gap = 96
+    ooff = np.zeros(n, dtype=np.uint64)
+    ooff[1:] = np.cumsum(cap + gap)[:-1]
+    ooff += gap
+    total = int(ooff[-1] + cap[-1]) + gap
+    L = lzb.lib()
+    out = np.full(total, 0xA5, dtype=np.uint8)
+    out_len = np.zeros(n, dtype=np.uint64)
+    status = np.zeros(n, dtype=np.int32)
+    dec = lzb.Decoder()
+    rc = L.lzb_dec_code_batch(dec._h, arr.ctypes.data, off.ctypes.data, ln.ctypes.data, n, out.ctypes.data, ooff.ctypes.data,
+                              cap.ctypes.data, out_len.ctypes.data, status.ctypes.data)
+    dec.close()
+    assert rc == 1 and (status == 1).all()
+    keep = np.ones(total, dtype=bool)
+    for i in range(n):
+        a = int(ooff[i])
+        assert out[a: a + sizes[i]].tobytes() == blocks[i], i
+        keep[a: a + int(cap[i])] = False
+    assert (out[keep] == 0xA5).all()

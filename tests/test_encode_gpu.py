@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import FIREFOX
+from conftest import CLI_DEFAULTS, VECTORS
 
 pytestmark = pytest.mark.gpu
 
@@ -134,11 +134,19 @@ def test_encode_1mib_blocks_c3(lzb, oracle, corpus):
         assert np.array_equal(out[int(ooff[i]): int(ooff[i] + olen[i])], ref[int(roff[i]): int(roff[i] + rlen[i])]), i
 
 
-@pytest.mark.skipif(not os.path.exists(FIREFOX), reason="reference fixture only exists in the build container")
-def test_encode_firefox_golden_md5(lzb):
-    data = open(FIREFOX, "rb").read()
-    s = lzb.encode_alone(data)
-    assert len(s) == 138940 and hashlib.md5(s).hexdigest() == "93c6983fcfa73e55099a11ee13139687"
+@pytest.mark.parametrize("switch,kw,length,md5", VECTORS, ids=[v[0] or "default" for v in VECTORS])
+def test_encode_reference_golden_vectors(lzb, firefox, switch, kw, length, md5):
+    """The reference's own parity contract, LzmaAloneTest.java:27-38, straight through the CUDA path:
+    `LzmaAlone e firefox.exe <switch>` must produce exactly `length` bytes with this md5 (the Java
+    test's constants), and the GPU decoder must give the file back.  The input is the reference's
+    fixture (tests/golden/firefox.exe.xz on the GPU box, same md5)."""
+    p = dict(CLI_DEFAULTS)
+    p.update(kw)
+    s = lzb.encode_alone(firefox, **p)
+    assert len(s) == length
+    assert hashlib.md5(s).hexdigest() == md5
+    ok, back = lzb.decode_alone(s)
+    assert ok and back == firefox
 
 
 def test_roundtrip_gpu_encode_gpu_decode(lzb, corpus):
@@ -237,3 +245,39 @@ def test_reference_learning_test_inputs(lzb, oracle):
         ok, back = oracle.decode(oracle.props_bytes(p), payload, len(data))
         assert ok == 1 and back == data
     enc.close()
+
+
+def _batch_equals_oracle(lzb, oracle, p, data, n, size, threads=8):
+    off = np.arange(n, dtype=np.uint64) * size
+    ln = np.full(n, size, dtype=np.uint64)
+    ref, roff, rlen = oracle.encode_batch(data, off, ln, oracle.props(**p), True, threads)
+    enc = _encoder(lzb, p)
+    out, ooff, olen = enc.code_batch(data, off, ln, with_header=True)
+    enc.close()
+    assert np.array_equal(olen, rlen)
+    for i in range(n):
+        assert np.array_equal(out[int(ooff[i]): int(ooff[i] + olen[i])], ref[int(roff[i]): int(roff[i] + rlen[i])]), i
+    dec = lzb.Decoder()
+    cap = np.full(n, size + 273, dtype=np.uint64)
+    doff = np.arange(n, dtype=np.uint64) * (size + 273)
+    dout, dlen, status = dec.code_batch(out, ooff, olen, doff, cap)
+    dec.close()
+    assert (status == 1).all() and (dlen == size).all()
+    assert np.array_equal(dout.reshape(n, size + 273)[:, :size].reshape(-1), data)
+
+
+def test_encode_4mib_blocks_c5(lzb, oracle, corpus):
+    """BASELINE config 5 shape: 4 MiB blocks, dict 4 MiB, fb 32, the mixed class cycle (8 blocks = two of
+    each class): every block == oracle, and the GPU decoder gives the corpus back."""
+    p = dict(BASE)
+    p.update(dict_size=1 << 22, fb=32)
+    n, size = 8, 1 << 22
+    _batch_equals_oracle(lzb, oracle, p, corpus.generate(size, n, corpus.MIXED, 5), n, size)
+
+
+def test_encode_8mib_blocks_c4_all_classes(lzb, oracle, corpus):
+    """BASELINE config 4 shape on every corpus class: 8 MiB blocks, dict 8 MiB, fb 273 (max-ratio settings)."""
+    p = dict(BASE)
+    p.update(dict_size=1 << 23, fb=273)
+    n, size = 4, 1 << 23
+    _batch_equals_oracle(lzb, oracle, p, corpus.generate(size, n, corpus.MIXED, 4), n, size, threads=4)

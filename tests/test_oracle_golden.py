@@ -12,26 +12,9 @@ import os
 import numpy as np
 import pytest
 
-from conftest import FIREFOX
+from conftest import CLI_DEFAULTS, FIREFOX, FIREFOX_XZ, VECTORS  # noqa: F401
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-
-# (switch, overrides of the CLI defaults d23 lc3 lp0 pb2 fb128 bt4, length, md5) -- LzmaAloneTest.java:27-38
-VECTORS = [
-    ("", {}, 138940, "93c6983fcfa73e55099a11ee13139687"),
-    ("-eos", {"eos": True}, 138946, "4b9287512dcf72b094abafbd5fbfda85"),
-    ("-d0", {"dict_size": 1}, 356822, "385ef9694b5d0640fd372c99cec1d575"),
-    ("-fb5", {"fb": 5}, 150508, "81b9ab49744b242c4e5a0274ae5a83d3"),
-    ("-fb273", {"fb": 273}, 138711, "44e59bfa0128c6dcfde164598e180e92"),
-    ("-lc0", {"lc": 0}, 143351, "8ebbd8dc6c1a1dd2c1803659a4a2b978"),
-    ("-lc8", {"lc": 8}, 144829, "f7a9f4ce9c7853c07445b41cca75c58c"),
-    ("-lp1", {"lp": 1}, 137620, "27fba851ee64468dc5391d4a0f430ab7"),
-    ("-lp4", {"lp": 4}, 141530, "377337634457f7017760e45129760c7d"),
-    ("-pb0", {"pb": 0}, 142879, "563da117b34b52358e24d6e5b16d093d"),
-    ("-pb4", {"pb": 4}, 140046, "cbbff9f4722065bec54336a7d3d49832"),
-    ("-mfbt2", {"mf": 0}, 138877, "126f88731f968265bf163b7f7b5521db"),
-]
-CLI_DEFAULTS = dict(dict_size=1 << 23, lc=3, lp=0, pb=2, fb=128, mf=1, eos=False)
 
 
 def _rc_bits(O, bits):
@@ -76,11 +59,17 @@ def test_prob_prices_table(oracle):  # ProbPrices.java:8-18, SURVEY App. A #13
     assert (t[0], t[1], t[2], t[3], t[4], t[128], t[256], t[511]) == (0, 576, 512, 480, 448, 128, 64, 0)
 
 
-@pytest.mark.skipif(not os.path.exists(FIREFOX), reason="reference fixture only exists in the build container")
+def test_packed_fixture_is_the_reference_file():
+    """tests/golden/firefox.exe.xz unpacks to the reference's own test input (checked wherever both exist)."""
+    packed = lzma.decompress(open(FIREFOX_XZ, "rb").read())
+    assert len(packed) == 916960 and hashlib.md5(packed).hexdigest() == "5744fff8e72d105c138dae9e17bb29fe"
+    if os.path.exists(FIREFOX):
+        assert packed == open(FIREFOX, "rb").read()
+
+
 @pytest.mark.parametrize("switch,kw,length,md5", VECTORS, ids=[v[0] or "default" for v in VECTORS])
-def test_firefox_golden_vectors(oracle, switch, kw, length, md5):
-    data = open(FIREFOX, "rb").read()
-    assert hashlib.md5(data).hexdigest() == "5744fff8e72d105c138dae9e17bb29fe"
+def test_firefox_golden_vectors(oracle, firefox, switch, kw, length, md5):
+    data = firefox
     d = dict(CLI_DEFAULTS)
     d.update(kw)
     s = oracle.encode(data, oracle.props(**d), alone=True)
