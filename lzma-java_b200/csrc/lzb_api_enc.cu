@@ -27,7 +27,7 @@ struct lzb_enc {
     DevBuf d_in, d_out, d_meta;
     PinBuf h_meta;
     // developer / test hooks (DESIGN.md "test hooks"), read ONCE when the handle is created
-    int32_t tune_warps = 0, tune_pair_mul = 0;
+    int32_t tune_warps = 0, tune_pair_mul = 0, tune_lit = -1;
     bool tune_fifo = false, tune_timing = false;
 };
 
@@ -46,6 +46,7 @@ lzb_enc* lzb_enc_create(int device) {
     }
     if (const char* v = getenv("LZB_ENC_WARPS")) e->tune_warps = atoi(v) > 0 ? atoi(v) : 0;
     if (const char* v = getenv("LZB_PAIR_MUL")) e->tune_pair_mul = atoi(v) > 0 ? atoi(v) : 0;
+    if (const char* v = getenv("LZB_ENC_LIT")) e->tune_lit = v[0] == 's' ? 0 : v[0] == 'g' ? 1 : -1;  // smem / global
     e->tune_fifo = getenv("LZB_ENC_FIFO") != nullptr;
     e->tune_timing = getenv("LZB_ENC_TIMING") != nullptr;
     return e;
@@ -139,6 +140,7 @@ int lzb_enc_code_batch_device(lzb_enc* e, const uint8_t* d_in, const uint64_t* d
     a.with_header = with_header13 != 0;
     a.tune_warps = e->tune_warps;
     a.tune_pair_mul = e->tune_pair_mul;
+    a.tune_lit = e->tune_lit;
     a.tune_fifo = e->tune_fifo;
     a.tune_timing = e->tune_timing;
     int launches = 0;

@@ -141,7 +141,7 @@ void bind_wave(const EncodeArgs& a, const Plan& P, uint8_t* mf_base, uint8_t* li
     pa->eos = a.eos;
     pa->with_header = a.with_header;
     pa->slice_bytes = P.geo.slice_bytes;
-    pa->slice_budget = P.geo.slice_budget;
+    pa->lit_in_smem = P.geo.lit_in_smem;
 }
 
 cudaError_t grow(EncScratch& scratch, size_t need, cudaStream_t st) {
@@ -195,16 +195,18 @@ cudaError_t run_waves(const EncodeArgs& a, const Plan& P, EncScratch& scratch, i
         uint32_t* order_dev = nullptr;
         bind_wave(a, P, (uint8_t*)scratch.p, list_base, first + done, wb, pair_cap, slots, &w, &pa, &mf_zero, &list_zero, &order_dev);
         // LZB_ENC_TIMING=1 (developer hook): phase times of every wave on stderr
-        cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};
+        cudaEvent_t tev[3] = {nullptr, nullptr, nullptr}, mev[4] = {nullptr, nullptr, nullptr, nullptr};
         if (P.timing) {
             for (auto& x : tev) cudaEventCreate(&x);
+            for (auto& x : mev) cudaEventCreate(&x);
             cudaEventRecord(tev[0], st);
         }
         e = cudaMemsetAsync(scratch.p, 0, mf_zero, st);
         if (e != cudaSuccess) return e;
         e = cudaMemsetAsync(list_base, 0, list_zero, st);
         if (e != cudaSuccess) return e;
-        e = launch_mf(w, (uint32_t)a.max_in_len, num_sms, st);
+        if (P.timing) cudaEventRecord(mev[0], st);
+        e = launch_mf(w, (uint32_t)a.max_in_len, num_sms, st, P.timing ? mev + 1 : nullptr);
         if (e != cudaSuccess) return e;
         *nl += a.max_in_len ? 3 : 1;
 
@@ -217,8 +219,10 @@ cudaError_t run_waves(const EncodeArgs& a, const Plan& P, EncScratch& scratch, i
         if (P.timing) cudaEventRecord(tev[1], st);
         if (overflow >= 2) return cudaErrorInvalidValue;  // a block longer than the declared max_in_len
         if (overflow) {
-            if (P.timing)
+            if (P.timing) {
                 for (auto& x : tev) cudaEventDestroy(x);
+                for (auto& x : mev) cudaEventDestroy(x);
+            }
             if (pair_mul >= 512) return cudaErrorMemoryAllocation;
             pair_mul *= 2;
             continue;
@@ -236,10 +240,11 @@ cudaError_t run_waves(const EncodeArgs& a, const Plan& P, EncScratch& scratch, i
             return cudaSuccess;
         }
         pa.mf = w;
-        int warps = (int)((wb + (uint32_t)num_sms - 1) / (uint32_t)num_sms);
+        // one CTA per SM (every SM gets work, blocks are drawn by ticket), as many warps as the wave can fill
+        const int grid = (int)std::min<uint32_t>(wb, (uint32_t)num_sms);
+        int warps = (int)((wb + (uint32_t)grid - 1) / (uint32_t)grid);
         warps = std::min(std::max(warps, 1), P.geo.max_warps);
         if (a.tune_warps > 0) warps = std::min((int)a.tune_warps, P.geo.max_warps);  // tuning knob
-        const int grid = (int)std::min<uint32_t>((wb + (uint32_t)warps - 1) / (uint32_t)warps, (uint32_t)num_sms);
         // More blocks than parser slots: a block that starts late must not be a slow one, or the wave
         // ends on it with the GPU idle.  The parser's cost grows with the bytes to code and with the
         // match pairs it has to price, so blocks are handed out by decreasing (length + pair words).
@@ -271,12 +276,18 @@ cudaError_t run_waves(const EncodeArgs& a, const Plan& P, EncScratch& scratch, i
         if (P.timing) {
             cudaEventRecord(tev[2], st);
             cudaEventSynchronize(tev[2]);
-            float t_mf = 0, t_parse = 0;
+            float t_mf = 0, t_parse = 0, t_link = 0, t_tree = 0, t_long = 0;
             cudaEventElapsedTime(&t_mf, tev[0], tev[1]);
             cudaEventElapsedTime(&t_parse, tev[1], tev[2]);
-            fprintf(stderr, "lzb_enc wave: %u blocks (max %llu B), %d warps x %d CTAs, match finder %.1f ms, parse %.1f ms\n", wb,
-                    (unsigned long long)a.max_in_len, warps, grid, t_mf, t_parse);
+            if (a.max_in_len) {
+                cudaEventElapsedTime(&t_link, mev[0], mev[1]);
+                cudaEventElapsedTime(&t_tree, mev[1], mev[2]);
+                cudaEventElapsedTime(&t_long, mev[2], mev[3]);
+            }
+            fprintf(stderr, "lzb_enc wave: %u blocks (max %llu B), %d warps x %d CTAs, match finder %.1f ms (link %.1f tree %.1f long %.1f), parse %.1f ms\n",
+                    wb, (unsigned long long)a.max_in_len, warps, grid, t_mf, t_link, t_tree, t_long, t_parse);
             for (auto& x : tev) cudaEventDestroy(x);
+            for (auto& x : mev) cudaEventDestroy(x);
         }
         done += wb;
         if (done < count) {  // the next wave reuses the scratch
@@ -308,7 +319,10 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
     P.np = (uint32_t)a.max_in_len + 1;
     P.dic_log = 0;
     while ((uint32_t)a.dict_size > (1u << P.dic_log)) P.dic_log++;  // Encoder.java:1141-1144
-    P.geo = parse_geometry(a.lc, a.lp, a.pb, a.fb);
+    // streams per SM and where the literal coders live follow from how many blocks want to run at once
+    uint32_t per_sm = (a.n + (uint32_t)num_sms - 1) / (uint32_t)num_sms;
+    if (a.tune_warps > 0) per_sm = std::min<uint32_t>(per_sm, (uint32_t)a.tune_warps);
+    P.geo = parse_geometry(a.lc, a.lp, a.pb, a.fb, per_sm, a.tune_lit);
     P.lit_per_slot = P.geo.lit_in_smem ? 0 : ((size_t)0x300 << (a.lc + a.lp));
     P.timing = a.tune_timing;
 

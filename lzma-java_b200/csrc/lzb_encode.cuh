@@ -75,19 +75,19 @@ struct ParseArgs {
     int32_t lc, lp, pb, fb;
     bool eos, with_header;
     uint32_t slice_bytes;    // shared memory per warp
-    uint32_t slice_budget;   // literal coders stay in shared memory while the slice fits this budget
+    bool lit_in_smem;        // literal coders in the warp's slice (else in lit_scratch)
 };
 
 struct ParseGeometry {
-    uint32_t slice_bytes, slice_budget, cta_table_bytes;
+    uint32_t slice_bytes, cta_table_bytes;
     int max_warps;           // streams resident per SM
     bool lit_in_smem;
 };
 
 cudaError_t upload_mf_tables();
-cudaError_t launch_mf(const MfWave& w, uint32_t max_len, int num_sms, cudaStream_t st);
+cudaError_t launch_mf(const MfWave& w, uint32_t max_len, int num_sms, cudaStream_t st, cudaEvent_t* ev = nullptr);
 cudaError_t launch_parse(const ParseArgs& a, int grid, int warps, cudaStream_t st);
-ParseGeometry parse_geometry(int lc, int lp, int pb, int fb);
+ParseGeometry parse_geometry(int lc, int lp, int pb, int fb, uint32_t blocks_per_sm, int force_lit);
 size_t parse_opt_bytes_per_slot();
 
 }  // namespace lzb

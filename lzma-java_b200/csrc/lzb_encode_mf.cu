@@ -132,6 +132,34 @@ __global__ void __launch_bounds__(128) lzb_mf_link_kernel(MfWave w) {
     }
 }
 
+// ---- byte-run comparison, eight bytes per step ---------------------------------
+// The descent compares the window at the new position with the window at a candidate, starting
+// at the length both are already known to share (BinTree.java:244-248: a byte loop).  A byte loop
+// costs one dependent load round trip per byte; this reads both windows as unaligned 64-bit words
+// (two aligned loads + a funnel shift) and finds the first differing byte with one ffs.
+// Only aligned words that contain a byte the byte loop could have read are touched.
+__device__ __forceinline__ uint64_t load_u64_at(const uint8_t* p) {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(p) & ~uintptr_t(7));
+    const unsigned s = (unsigned)(reinterpret_cast<uintptr_t>(p) & 7u) * 8u;
+    const uint64_t lo = w[0];
+    if (s == 0) return lo;
+    return (lo >> s) | (w[1] << (64u - s));
+}
+// first i in [len, limit] with a[i] != c[i] (or limit); `room` = bytes that exist from a[0] on (room >= limit), c < a
+__device__ __forceinline__ uint32_t extend_run(const uint8_t* a, const uint8_t* c, uint32_t len, uint32_t limit, uint32_t room) {
+    while (len < limit && len + 8 <= room) {
+        const uint64_t x = load_u64_at(a + len) ^ load_u64_at(c + len);
+        if (x) {
+            len += (uint32_t)(__ffsll((long long)x) - 1) >> 3;
+            return len < limit ? len : limit;
+        }
+        len += 8;
+    }
+    if (len > limit) len = limit;
+    while (len < limit && a[len] == c[len]) len++;
+    return len;
+}
+
 // ---- pieces shared by the two tree kernels ------------------------------------
 struct TreeBlock {
     const uint8_t* buf;  // buf[pos1] is the byte at 1-based position pos1
@@ -202,9 +230,7 @@ __device__ __forceinline__ void tree_store_list(const MfWave& w, const TreeBlock
                 uint32_t lim = s1 <= t.n ? t.n + 1 - s1 : 0;
                 if (lim > (uint32_t)w.fb) lim = (uint32_t)w.fb;
                 const uint8_t* a = t.buf + s1;
-                const uint8_t* c = a - dist - 1;
-                uint32_t k = 0;
-                while (k < lim && a[k] == c[k]) k++;
+                const uint32_t k = lim ? extend_run(a, a - dist - 1, 0, lim, t.n + 1 - s1) : 0;
                 t.pairs2_out[off + 1 + i] = (uint16_t)k;
             }
         } else {
@@ -264,8 +290,7 @@ __global__ void __launch_bounds__(256) lzb_mf_tree_kernel(MfWave w) {
             const uint2 kids = *reinterpret_cast<const uint2*>(son + 2 * cm);
             uint32_t len = len0 < len1 ? len0 : len1;
             if (pby1[len] == cur[len]) {
-                while (++len != len_limit)
-                    if (pby1[len] != cur[len]) break;
+                len = extend_run(cur, pby1, len + 1, len_limit, remaining);
                 if (max_len < len) {
                     max_len = len;
                     pairs[cnt++] = (len << kPairDistBits) | (pos1 - cm - 1);
@@ -329,12 +354,12 @@ __global__ void __launch_bounds__(256) lzb_mf_long_kernel(MfWave w) {
             const unsigned am = __ballot_sync(kFull, active);
             last = __shfl_sync(kFull, pos1, 31 - __clz(am));
 
-            uint32_t len_limit = 0, match_min_pos = 0, max_len = 1, cnt = 0;
+            uint32_t len_limit = 0, match_min_pos = 0, max_len = 1, cnt = 0, remaining = 0;
             uint32_t ptr0 = 0, ptr1 = 0, len0 = direct, len1 = direct, cm = root;
             int32_t count = w.cut;
             bool done = !active;
             if (active) {
-                const uint32_t remaining = t.n - (pos1 - 1);
+                remaining = t.n - (pos1 - 1);
                 len_limit = remaining < (uint32_t)w.fb ? remaining : (uint32_t)w.fb;
                 match_min_pos = pos1 > w.cyclic_size ? pos1 - w.cyclic_size : 0;
                 tree_prepairs(w, t, pos1, root, match_min_pos, pairs, cnt, max_len);
@@ -358,10 +383,7 @@ __global__ void __launch_bounds__(256) lzb_mf_long_kernel(MfWave w) {
                         const uint8_t* pby1 = t.buf + cm;
                         if (!have_cmp) {
                             len = len0 < len1 ? len0 : len1;
-                            if (pby1[len] == cur[len]) {
-                                while (++len != len_limit)
-                                    if (pby1[len] != cur[len]) break;
-                            }
+                            if (pby1[len] == cur[len]) len = extend_run(cur, pby1, len + 1, len_limit, remaining);
                             have_cmp = true;
                         }
                         const bool full = len == len_limit && max_len < len;  // :249-256 ends the insertion
@@ -403,18 +425,22 @@ __global__ void __launch_bounds__(256) lzb_mf_long_kernel(MfWave w) {
     }
 }
 
-cudaError_t launch_mf(const MfWave& w, uint32_t max_len, int num_sms, cudaStream_t st) {
+// `ev` (optional, LZB_ENC_TIMING): three events recorded after the link, tree and long kernels
+cudaError_t launch_mf(const MfWave& w, uint32_t max_len, int num_sms, cudaStream_t st, cudaEvent_t* ev) {
     if (w.n_blocks == 0) return cudaSuccess;
     const uint32_t warps_per_cta = 4;
     lzb_mf_link_kernel<<<(w.n_blocks + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, st>>>(w);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (ev) cudaEventRecord(ev[0], st);
     if (max_len == 0) return cudaSuccess;
     dim3 grid((max_len + 255) / 256, w.n_blocks);
     lzb_mf_tree_kernel<<<grid, 256, 0, st>>>(w);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (ev) cudaEventRecord(ev[1], st);
     lzb_mf_long_kernel<<<num_sms * 8, 256, 0, st>>>(w);
+    if (ev) cudaEventRecord(ev[2], st);
     return cudaGetLastError();
 }
 

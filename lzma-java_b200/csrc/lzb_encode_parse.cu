@@ -88,53 +88,69 @@ __device__ __forceinline__ bool ln_prev1(uint32_t l) { return (l >> 28) & 1; }
 __device__ __forceinline__ bool ln_prev2(uint32_t l) { return (l >> 29) & 1; }
 
 // ---- range encoder (RangeEncoder.java:23-87) --------------------------------
-// The coder state is replicated in every lane (control flow stays uniform); only lane 0
-// stores output bytes.  A symbol is emitted as a batch: lane k prepares the k-th binary
-// decision (probability address + bit, or a direct bit), adapts its own probability --
-// all addresses of one symbol are distinct -- and the batch loop then folds the
-// decisions into low/range in order, fetching each (old probability, bit) by shuffle.
-struct RangeEnc {
+// The coder state lives in the warp's shared-memory slice and the emission routine is a real
+// (out-of-line) function: the parser reaches it from seven places, and seven inlined copies were
+// 16 KB of a kernel whose hot path must fit a 32 KB instruction cache (parser).  It takes
+// values and a shared-memory pointer only -- nothing of the caller's register state has its address
+// taken.  A symbol is emitted as a batch: lane k passes the k-th binary decision (probability
+// address + bit, or a direct bit); the routine adapts the probabilities -- all addresses of one
+// symbol are distinct -- and folds the decisions into low/range in order, fetching each
+// (old probability, bit) by shuffle.  Every lane runs the same fold; lane 0 stores the bytes.
+struct __align__(16) RcState {
     uint64_t low;
-    uint32_t range;
-    uint32_t cache_size;
-    uint32_t cache;
+    uint32_t range, cache_size;
+    uint32_t cache, pos;  // pos = bytes produced so far (may run past cap: then nothing is stored)
+    uint32_t cap, pad;
     uint8_t* out;
-    uint64_t pos, cap;
-    int lane;
+};
 
-    __device__ __forceinline__ void init(uint8_t* o, uint64_t c, int l) {
-        low = 0;
-        range = 0xFFFFFFFFu;
-        cache_size = 1;
-        cache = 0;
-        out = o;
-        pos = 0;
-        cap = c;
-        lane = l;
+__device__ __forceinline__ void rc_init(RcState* rs, uint8_t* out, uint64_t cap, int lane) {  // RangeEncoder.java:23-29
+    if (lane == 0) {
+        rs->low = 0;
+        rs->range = 0xFFFFFFFFu;
+        rs->cache_size = 1;
+        rs->cache = 0;
+        rs->pos = 0;
+        rs->cap = cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)cap;
+        rs->out = out;
     }
-    // RangeEncoder.shiftLow (:73-87).  Inline on purpose: an out-of-line call would take the address
-    // of the coder state and push the whole parser state into local memory.
-    __device__ __forceinline__ void shift_low() {
-        const uint32_t low_hi = (uint32_t)(low >> 32);
-        if (low_hi != 0 || low < 0xFF000000ull) {
-            uint32_t temp = cache;
+    __syncwarp();
+}
+
+// RangeEncoder.shiftLow (:73-87)
+#define LZB_SHIFT_LOW()                                                            \
+    do {                                                                           \
+        const uint32_t low_hi = (uint32_t)(low >> 32);                             \
+        if (low_hi != 0 || low < 0xFF000000ull) {                                  \
+            uint32_t temp = cache;                                                 \
+            _Pragma("unroll 1") do {                                               \
+                if (lane == 0 && pos < cap) out[pos] = (uint8_t)(temp + low_hi);   \
+                pos++;                                                             \
+                temp = 0xFF;                                                       \
+            } while (--cache_size != 0);                                           \
+            cache = ((uint32_t)low) >> 24;                                         \
+        }                                                                          \
+        cache_size++;                                                              \
+        low = (low & 0xFFFFFF) << 8;                                               \
+    } while (0)
+
+// Encode `cnt` (<= 32) decisions.  Lane k < cnt passes its decision: `prob` (ignored for a direct
+// bit) and bd = bit | direct << 1.  RangeEncoder.encode :38-54 / encodeDirectBits :56-67.
+__device__ __noinline__ void rc_batch(RcState* rs, int cnt, uint16_t* prob, uint32_t bd, int lane) {
+    uint32_t p = 0;
+    const uint32_t bit = bd & 1u;
+    if (lane < cnt && !(bd & 2u)) {
+        p = *prob;
+        *prob = (uint16_t)(bit ? p - (p >> kNumMoveBits) : p + ((kBitModelTotal - p) >> kNumMoveBits));
+    }
+    const uint32_t w = p | (bd << 16);  // old probability | bit << 16 | direct << 17
+    uint64_t low = rs->low;
+    uint32_t range = rs->range, cache_size = rs->cache_size, cache = rs->cache, pos = rs->pos;
+    const uint32_t cap = rs->cap;
+    uint8_t* out = rs->out;
 #pragma unroll 1
-            do {
-                if (lane == 0 && pos < cap) out[pos] = (uint8_t)(temp + low_hi);
-                pos++;
-                temp = 0xFF;
-            } while (--cache_size != 0);
-            cache = ((uint32_t)low) >> 24;
-        }
-        cache_size++;
-        low = (low & 0xFFFFFF) << 8;
-    }
-    __device__ __forceinline__ void flush() {  // :31-36
-#pragma unroll 1
-        for (int i = 0; i < 5; i++) shift_low();
-    }
-    // fold one decision (old probability | bit << 16 | direct << 17) into low / range
-    __device__ __forceinline__ void step(uint32_t e) {
+    for (int k = 0; k < cnt; k++) {
+        const uint32_t e = __shfl_sync(kFull, w, k);
         if (e & 0x20000u) {
             range >>= 1;
             if (e & 0x10000u) low += range;
@@ -149,62 +165,88 @@ struct RangeEnc {
         }
         if (range < kTopValue) {
             range <<= 8;
-            shift_low();
+            LZB_SHIFT_LOW();
         }
     }
-    // Encode `cnt` (<= 32) decisions.  Lane k < cnt passes its decision: `prob` (ignored for a
-    // direct bit), `bit`, `direct`.  RangeEncoder.encode :38-54 / encodeDirectBits :56-67.
-    __device__ __forceinline__ void batch(int cnt, uint16_t* prob, uint32_t bit, bool direct) {
-        uint32_t p = 0;
-        if (lane < cnt && !direct) {
-            p = *prob;
-            *prob = (uint16_t)(bit ? p - (p >> kNumMoveBits) : p + ((kBitModelTotal - p) >> kNumMoveBits));
-        }
-        const uint32_t w = p | (bit << 16) | ((uint32_t)direct << 17);
-        // one rolled loop, one copy of the coder step: the emission code is executed by every warp
-        // of the SM at different times, and unrolling it (x4, shuffles hoisted) cost more in
-        // instruction-cache misses at 7-8 streams per SM than the shuffle latency it hid
+    if (lane == 0) {
+        rs->low = low;
+        rs->range = range;
+        rs->cache_size = cache_size;
+        rs->cache = cache;
+        rs->pos = pos;
+    }
+    __syncwarp();
+}
+
+__device__ __noinline__ void rc_flush(RcState* rs, int lane) {  // RangeEncoder.flush :31-36
+    uint64_t low = rs->low;
+    uint32_t cache_size = rs->cache_size, cache = rs->cache, pos = rs->pos;
+    const uint32_t cap = rs->cap;
+    uint8_t* out = rs->out;
 #pragma unroll 1
-        for (int k = 0; k < cnt; k++) step(__shfl_sync(kFull, w, k));
-        __syncwarp();
+    for (int i = 0; i < 5; i++) LZB_SHIFT_LOW();
+    if (lane == 0) {
+        rs->low = low;
+        rs->cache_size = cache_size;
+        rs->cache = cache;
+        rs->pos = pos;
     }
+    __syncwarp();
+}
+
+// What the out-of-line helpers (price-table refreshes) need to know about a stream; written once
+// per stream into the warp's slice so that they take one pointer instead of the parser's registers.
+struct __align__(16) WarpCtx {
+    RcState rc;
+    const uint16_t* prob_prices;  // CtaTables::prob_prices
+    const uint8_t* fast_pos;
+    uint16_t* model;
+    uint16_t* dist_prices;
+    uint16_t* slot_prices;
+    uint16_t* align_prices;
+    uint16_t* len_prices;
+    int32_t* len_counters;
+    int32_t pb, table_size, dist_table_size;
+    int32_t off_len, off_rep_len, off_pos_slot, off_pos_dec, off_pos_align;
 };
 
 // ---- shared-memory slice of one warp ----------------------------------------
 struct SliceLayout {
-    uint32_t dist_prices, slot_prices, align_prices, len_prices, len_counters, md, md2, ring, total;  // byte offsets
+    uint32_t ctx, dist_prices, slot_prices, align_prices, len_prices, len_counters, md, md2, ring, total;  // byte offsets
     uint32_t ring_nodes;
     bool lit_in_smem;
 };
-__host__ __device__ inline SliceLayout make_slice(int lc, int lp, int pb, int fb, uint32_t budget) {
+// `with_lit`: the literal coders (0x300 << (lc + lp) probabilities) follow the fixed part of the model in
+// shared memory; otherwise they live in global memory (ParseArgs::lit_scratch) and the slice shrinks
+// by 12 KB at lc + lp = 3, which is what bounds the streams per SM.
+__host__ __device__ inline SliceLayout make_slice(int lc, int lp, int pb, int fb, bool with_lit) {
     const ModelLayout L = make_layout(lc, lp, pb);
     const uint32_t table = (uint32_t)(fb - 1);
     // a DP step touches nodes [cur - 2fb - 1, cur + 2fb + 1]
     const uint32_t ring_nodes = ((uint32_t)(4 * fb + 3) + 31) & ~31u;
     SliceLayout s;
-    for (int with_lit = 1; with_lit >= 0; with_lit--) {
-        uint32_t o = (uint32_t)(L.n_fixed + (with_lit ? L.n_literal : 0)) * 2;
-        o = (o + 15) & ~15u;
-        s.dist_prices = o;  o += 512 * 2;
-        s.slot_prices = o;  o += 256 * 2;
-        s.align_prices = o; o += 16 * 2;
-        s.len_prices = o;   o += ((2u << pb) * table * 2 + 15) & ~15u;
-        s.len_counters = o; o += 32 * 4;
-        s.md = o;           o += 288 * 4;
-        s.md2 = o;          o += 288 * 2;
-        o = (o + 15) & ~15u;
-        s.ring = o;         o += ring_nodes * 32;
-        s.total = o;
-        s.ring_nodes = ring_nodes;
-        s.lit_in_smem = with_lit != 0;
-        if (s.total <= budget || !with_lit) break;
-    }
+    uint32_t o = (uint32_t)(L.n_fixed + (with_lit ? L.n_literal : 0)) * 2;
+    o = (o + 15) & ~15u;
+    s.ctx = o;          o += (uint32_t)sizeof(WarpCtx);
+    o = (o + 15) & ~15u;
+    s.dist_prices = o;  o += 512 * 2;
+    s.slot_prices = o;  o += 256 * 2;
+    s.align_prices = o; o += 16 * 2;
+    s.len_prices = o;   o += ((2u << pb) * table * 2 + 15) & ~15u;
+    s.len_counters = o; o += 32 * 4;
+    s.md = o;           o += 288 * 4;
+    s.md2 = o;          o += 288 * 2;
+    o = (o + 15) & ~15u;
+    s.ring = o;         o += ring_nodes * 32;
+    s.total = o;
+    s.ring_nodes = ring_nodes;
+    s.lit_in_smem = with_lit;
     return s;
 }
 
 // InWindow.GetMatchLen (InWindow.java:120-134) from absolute position `s`, 32 bytes per round;
 // every lane returns the same value.  Out of line: it is the rare continuation of a bitmap run.
-__device__ __forceinline__ int warp_match_len(const uint8_t* data, uint32_t n, int lane, uint32_t s, uint32_t distance, int limit) {
+__device__ __noinline__ int warp_match_len(const uint8_t* data, uint32_t n, int lane, uint32_t s, uint32_t distance, int limit) {
     if (limit > 0 && s + (uint32_t)limit > n) limit = (int)(n - s);
     const uint8_t* a = data + s;
     const uint8_t* b = a - distance - 1;
@@ -239,6 +281,95 @@ __device__ __forceinline__ void set4(T (&a)[4], int i, T v) {
     if (i == 3) a[3] = v;
 }
 
+// ---- price-table refreshes, out of line (rare: every fb-1 length symbols / 128 matches / 16 aligned
+// distances) -- LenEncoder.SetPrices (LenEncoder.java:50-71) + LenPriceTableEncoder.UpdateTable (:20-23),
+// Encoder.FillDistancesPrices / FillAlignPrices (Encoder.java:1087-1125).  One lane per table entry.
+__device__ __forceinline__ uint32_t ctx_price_bit(const uint16_t* pp, uint32_t prob, uint32_t bit) {  // ProbPrices.java:23-37
+    return pp[(((prob - bit) ^ (0u - bit)) & (kBitModelTotal - 1)) >> 2];
+}
+__device__ __forceinline__ uint32_t ctx_tree_price(const uint16_t* pp, const uint16_t* probs, int nbits, uint32_t symbol) {  // BitTreeEncoder.java:38-48
+    uint32_t price = 0, mm = 1;
+    #pragma unroll 1
+    for (int bi = nbits; bi != 0;) {
+        bi--;
+        const uint32_t bit = (symbol >> bi) & 1;
+        price += ctx_price_bit(pp, probs[mm], bit);
+        mm = (mm << 1) + bit;
+    }
+    return price;
+}
+__device__ __forceinline__ uint32_t ctx_reverse_price(const uint16_t* pp, const uint16_t* probs, int nbits, uint32_t symbol) {  // :50-60
+    uint32_t price = 0, mm = 1;
+    #pragma unroll 1
+    for (int i = nbits; i != 0; i--) {
+        const uint32_t bit = symbol & 1;
+        symbol >>= 1;
+        price += ctx_price_bit(pp, probs[mm], bit);
+        mm = (mm << 1) | bit;
+    }
+    return price;
+}
+
+__device__ __noinline__ void ctx_len_update_table(const WarpCtx* c, int which, uint32_t ps, int lane) {
+    __syncwarp();
+    const uint16_t* pp = c->prob_prices;
+    const int pb = c->pb, table_size = c->table_size;
+    const uint16_t* lp_ = c->model + (which ? c->off_rep_len : c->off_len);
+    uint16_t* prices = c->len_prices + ((which << pb) + ps) * table_size;
+    const uint32_t a0 = pp[lp_[0] >> 2], a1 = pp[(kBitModelTotal - lp_[0]) >> 2];
+    const uint32_t b0 = a1 + pp[lp_[1] >> 2], b1 = a1 + pp[(kBitModelTotal - lp_[1]) >> 2];
+    #pragma unroll 1
+    for (int i = lane; i < table_size; i += 32) {
+        uint32_t v;
+        if (i < kNumLowLenSymbols) v = a0 + ctx_tree_price(pp, lp_ + len_low(pb, ps), kNumLowLenBits, i);
+        else if (i < kNumLowLenSymbols + kNumMidLenSymbols) v = b0 + ctx_tree_price(pp, lp_ + len_mid(pb, ps), kNumMidLenBits, i - kNumLowLenSymbols);
+        else v = b1 + ctx_tree_price(pp, lp_ + len_high(pb), kNumHighLenBits, i - kNumLowLenSymbols - kNumMidLenSymbols);
+        prices[i] = (uint16_t)v;
+    }
+    if (lane == 0) c->len_counters[which * 16 + ps] = table_size;
+    __syncwarp();
+}
+
+__device__ __noinline__ void ctx_fill_distances_prices(const WarpCtx* c, int lane) {
+    __syncwarp();
+    const uint16_t* pp = c->prob_prices;
+    const uint16_t* model = c->model;
+    uint16_t* slot_prices = c->slot_prices;
+    const int dist_table_size = c->dist_table_size;
+    // slot prices first (they do not depend on tempPrices)
+    #pragma unroll 1
+    for (int k = lane; k < kNumLenToPosStates * dist_table_size; k += 32) {
+        const int lps = k / dist_table_size, slot = k - lps * dist_table_size;
+        uint32_t v = ctx_tree_price(pp, model + c->off_pos_slot + (lps << kNumPosSlotBits), kNumPosSlotBits, slot);
+        if (slot >= kEndPosModelIndex) v += (uint32_t)((((slot >> 1) - 1) - kNumAlignBits) << kNumBitPriceShiftBits);
+        slot_prices[(lps << kNumPosSlotBits) + slot] = (uint16_t)v;
+    }
+    __syncwarp();
+    #pragma unroll 1
+    for (int k = lane; k < kNumLenToPosStates * kNumFullDistances; k += 32) {
+        const int lps = k >> 7, i = k & (kNumFullDistances - 1);
+        uint32_t v;
+        if (i < kStartPosModelIndex) {
+            v = slot_prices[(lps << kNumPosSlotBits) + i];
+        } else {
+            const int slot = c->fast_pos[i];  // getPosSlot, i < 2^11 (Encoder.java:86-94)
+            const int footer = (slot >> 1) - 1;
+            const int base = (2 | (slot & 1)) << footer;
+            v = (uint32_t)slot_prices[(lps << kNumPosSlotBits) + slot] +
+                ctx_reverse_price(pp, model + c->off_pos_dec + base - slot - 1, footer, i - base);
+        }
+        c->dist_prices[lps * kNumFullDistances + i] = (uint16_t)v;
+    }
+    __syncwarp();
+}
+
+__device__ __noinline__ void ctx_fill_align_prices(const WarpCtx* c, int lane) {
+    __syncwarp();
+    if (lane < kAlignTableSize)
+        c->align_prices[lane] = (uint16_t)ctx_reverse_price(c->prob_prices, c->model + c->off_pos_align, kNumAlignBits, lane);
+    __syncwarp();
+}
+
 // ---- everything one stream needs (identical in every lane unless noted) -----
 struct Enc {
     const CtaTables* T;
@@ -264,7 +395,7 @@ struct Enc {
     int lc, lp, pb, fb, table_size, dist_table_size;
     uint32_t pos_mask, lp_mask;
     bool eos;
-    RangeEnc rc;            // meaningful in lane 0 only
+    WarpCtx* ctx;           // shared: range-coder state + what the out-of-line helpers need
     uint32_t m;             // match-finder cursor, 0-based (== _pos - 1 of the reference's InWindow)
     const uint16_t* pairs2;
     uint32_t pf_pos, pf_cnt, pf_pair, pf_l2, pf_from;  // prefetched list (pf_pair / pf_l2 differ per lane)
@@ -286,28 +417,6 @@ struct Enc {
     }
     __device__ __forceinline__ uint32_t price0(uint32_t prob) const { return T->prob_prices[prob >> 2]; }
     __device__ __forceinline__ uint32_t price1(uint32_t prob) const { return T->prob_prices[(kBitModelTotal - prob) >> 2]; }
-    __device__ __forceinline__ uint32_t tree_price(const uint16_t* probs, int nbits, uint32_t symbol) const {  // BitTreeEncoder.java:38-48
-        uint32_t price = 0, mm = 1;
-        #pragma unroll 1
-        for (int bi = nbits; bi != 0;) {
-            bi--;
-            const uint32_t bit = (symbol >> bi) & 1;
-            price += price_bit(probs[mm], bit);
-            mm = (mm << 1) + bit;
-        }
-        return price;
-    }
-    __device__ __forceinline__ uint32_t reverse_price(const uint16_t* probs, int nbits, uint32_t symbol) const {  // :50-60
-        uint32_t price = 0, mm = 1;
-        #pragma unroll 1
-        for (int i = nbits; i != 0; i--) {
-            const uint32_t bit = symbol & 1;
-            symbol >>= 1;
-            price += price_bit(probs[mm], bit);
-            mm = (mm << 1) | bit;
-        }
-        return price;
-    }
     __device__ __forceinline__ int pos_slot(uint32_t pos) const {  // Encoder.java:86-94
         if (pos < (1u << 11)) return T->fast_pos[pos];
         if (pos < (1u << 21)) return T->fast_pos[pos >> 10] + 20;
@@ -438,24 +547,7 @@ struct Enc {
     __device__ __forceinline__ uint32_t len_price(int which, int symbol, uint32_t ps) const {
         return len_prices[((which << pb) + ps) * table_size + symbol];
     }
-    // LenEncoder.SetPrices :50-71 + UpdateTable :20-23, one lane per symbol
-    __device__ __forceinline__ void len_update_table(int which, uint32_t ps) {
-        __syncwarp();
-        const uint16_t* lp_ = model + (which ? L.rep_len : L.len);
-        uint16_t* prices = len_prices + ((which << pb) + ps) * table_size;
-        const uint32_t a0 = price0(lp_[0]), a1 = price1(lp_[0]);
-        const uint32_t b0 = a1 + price0(lp_[1]), b1 = a1 + price1(lp_[1]);
-        #pragma unroll 1
-        for (int i = lane; i < table_size; i += 32) {
-            uint32_t v;
-            if (i < kNumLowLenSymbols) v = a0 + tree_price(lp_ + len_low(pb, ps), kNumLowLenBits, i);
-            else if (i < kNumLowLenSymbols + kNumMidLenSymbols) v = b0 + tree_price(lp_ + len_mid(pb, ps), kNumMidLenBits, i - kNumLowLenSymbols);
-            else v = b1 + tree_price(lp_ + len_high(pb), kNumHighLenBits, i - kNumLowLenSymbols - kNumMidLenSymbols);
-            prices[i] = (uint16_t)v;
-        }
-        if (lane == 0) len_counters[which * 16 + ps] = table_size;
-        __syncwarp();
-    }
+    __device__ __forceinline__ void len_update_table(int which, uint32_t ps) { ctx_len_update_table(ctx, which, ps, lane); }
     // all lanes, after the bits were emitted: LenPriceTableEncoder.encode :32-37
     __device__ __forceinline__ void len_count(int which, uint32_t ps) {
         const int c = len_counters[which * 16 + ps] - 1;
@@ -561,39 +653,13 @@ struct Enc {
         return price + len_price(0, len - kMatchMinLen, ps);
     }
 
-    // ---- price table refresh (Encoder.java:1087-1125), one lane per entry ----
+    // ---- price table refresh (Encoder.java:1087-1125): out of line, see ctx_fill_* ----
     __device__ __forceinline__ void fill_distances_prices() {
-        __syncwarp();
-        // slot prices first (they do not depend on tempPrices)
-        #pragma unroll 1
-        for (int k = lane; k < kNumLenToPosStates * dist_table_size; k += 32) {
-            const int lps = k / dist_table_size, slot = k - lps * dist_table_size;
-            uint32_t v = tree_price(model + L.pos_slot + (lps << kNumPosSlotBits), kNumPosSlotBits, slot);
-            if (slot >= kEndPosModelIndex) v += (uint32_t)((((slot >> 1) - 1) - kNumAlignBits) << kNumBitPriceShiftBits);
-            slot_prices[(lps << kNumPosSlotBits) + slot] = (uint16_t)v;
-        }
-        __syncwarp();
-        #pragma unroll 1
-        for (int k = lane; k < kNumLenToPosStates * kNumFullDistances; k += 32) {
-            const int lps = k >> 7, i = k & (kNumFullDistances - 1);
-            uint32_t v;
-            if (i < kStartPosModelIndex) {
-                v = slot_prices[(lps << kNumPosSlotBits) + i];
-            } else {
-                const int slot = pos_slot(i);
-                const int footer = (slot >> 1) - 1;
-                const int base = (2 | (slot & 1)) << footer;
-                v = (uint32_t)slot_prices[(lps << kNumPosSlotBits) + slot] + reverse_price(model + L.pos_dec + base - slot - 1, footer, i - base);
-            }
-            dist_prices[lps * kNumFullDistances + i] = (uint16_t)v;
-        }
-        __syncwarp();
+        ctx_fill_distances_prices(ctx, lane);
         match_price_count = 0;
     }
     __device__ __forceinline__ void fill_align_prices() {
-        __syncwarp();
-        if (lane < kAlignTableSize) align_prices[lane] = (uint16_t)reverse_price(model + L.pos_align, kNumAlignBits, lane);
-        __syncwarp();
+        ctx_fill_align_prices(ctx, lane);
         align_price_count = 0;
     }
 
@@ -673,8 +739,7 @@ struct Enc {
 
     __device__ __forceinline__ int get_optimum(uint32_t position, uint32_t* back_out);
     __device__ __forceinline__ void emit_match(uint32_t ps, int len, uint32_t pos, int slot);
-    __device__ __forceinline__ void flush_stream(uint32_t now);
-    __device__ __forceinline__ bool encode_one();
+    __device__ __forceinline__ bool encode_one(bool finish);
     __device__ __forceinline__ void run();
 };
 
@@ -1131,7 +1196,7 @@ __device__ __forceinline__ void Enc::emit_match(uint32_t ps, int len, uint32_t p
     if (lane >= cnt && lane < cnt + kNumPosSlotBits)
         tree_decision(lane - cnt, model + L.pos_slot + (len_to_pos_state(len) << kNumPosSlotBits), kNumPosSlotBits, (uint32_t)slot, ptr, bit);
     cnt += kNumPosSlotBits;
-    rc.batch(cnt, ptr, bit, false);
+    rc_batch(&ctx->rc, cnt, ptr, bit, lane);
     // batch 2: footer
     if (slot >= kStartPosModelIndex) {
         const int footer_bits = (slot >> 1) - 1;
@@ -1151,25 +1216,17 @@ __device__ __forceinline__ void Enc::emit_match(uint32_t ps, int len, uint32_t p
             }
             cnt = footer_bits;
         }
-        rc.batch(cnt, ptr, bit, direct);
+        rc_batch(&ctx->rc, cnt, ptr, bit | ((uint32_t)direct << 1), lane);
     }
 }
 
-__device__ __forceinline__ void Enc::flush_stream(uint32_t now) {  // Encoder.java:837-841 + WriteEndMarker :818-835
-    const uint32_t ps = now & pos_mask;
-    if (eos) {
-        // len = 2, posSlot = 63, posReduced = 2^30 - 1 (26 direct one-bits, align 15): pos - base with base = 3 << 30
-        emit_match(ps, kMatchMinLen, 0xFFFFFFFFu, (1 << kNumPosSlotBits) - 1);
-        state = st_match(state);
-    }
-    rc.flush();
-    __syncwarp();
-}
-
-// encodeOne (:890-936) with its emitters (:938-1024); false once the stream is flushed
-__device__ __forceinline__ bool Enc::encode_one() {
-    uint32_t back;
-    const int len = get_optimum(now_pos, &back);
+// encodeOne (:890-936) with its emitters (:938-1024); false once the input is used up.  With
+// `finish` it emits the end marker instead (WriteEndMarker :818-835: the match symbol with len 2,
+// posSlot 63 and an all-ones 32-bit "distance"), through the same emission code as every match.
+__device__ __forceinline__ bool Enc::encode_one(bool finish) {
+    uint32_t back = kNumRepDistances;
+    int len = kMatchMinLen;
+    if (!finish) len = get_optimum(now_pos, &back);
     const uint32_t ps = now_pos & pos_mask;
     __syncwarp();
     uint16_t* ptr = model;
@@ -1181,7 +1238,7 @@ __device__ __forceinline__ bool Enc::encode_one() {
         if (matched) mb = byte_at(0 - (int)rep_dist[0] - 1 - additional_offset);
         if (lane == 0) { ptr = p_is_match(state, ps); bit = 0; }
         else if (lane <= 8) literal_decision(lane - 1, lit_coder(now_pos, prev_byte), matched, mb, cur_byte, ptr, bit);
-        rc.batch(9, ptr, bit, false);
+        rc_batch(&ctx->rc, 9, ptr, bit, lane);
         prev_byte = cur_byte;
         state = st_lit(state);
     } else {
@@ -1202,7 +1259,7 @@ __device__ __forceinline__ bool Enc::encode_one() {
                 }
             }
             if (len != 1) cnt += len_decisions(lane - cnt, 1, (uint32_t)(len - kMatchMinLen), ps, ptr, bit);
-            rc.batch(cnt, ptr, bit, false);
+            rc_batch(&ctx->rc, cnt, ptr, bit, lane);
             if (len == 1) {
                 state = st_shortrep(state);
             } else {
@@ -1217,10 +1274,13 @@ __device__ __forceinline__ bool Enc::encode_one() {
                 rep_dist[0] = distance;
             }
         } else {  // encodeAMatch :976-1005
-            const uint32_t pos = back - kNumRepDistances;
-            const int slot = pos_slot(pos);
+            uint32_t pos = back - kNumRepDistances;
+            int slot = (1 << kNumPosSlotBits) - 1;
+            if (finish) pos = 0xFFFFFFFFu;  // posReduced = 2^30 - 1 (26 direct one-bits, align 15): pos - base with base = 3 << 30
+            else slot = pos_slot(pos);
             emit_match(ps, len, pos, slot);
             state = st_match(state);
+            if (finish) return false;
             len_count(0, ps);
             if (slot >= kEndPosModelIndex) align_price_count++;
             rep_dist[3] = rep_dist[2];
@@ -1236,10 +1296,7 @@ __device__ __forceinline__ bool Enc::encode_one() {
     if (additional_offset == 0) {
         if (match_price_count >= (1 << 7)) fill_distances_prices();
         if (align_price_count >= kAlignTableSize) fill_align_prices();
-        if (avail() == 0) {
-            flush_stream(now_pos);
-            return false;
-        }
+        if (avail() == 0) return false;
     }
     return true;
 }
@@ -1270,32 +1327,36 @@ __device__ __forceinline__ void Enc::run() {
         #pragma unroll 1
         for (uint32_t ps = 0; ps < (1u << pb); ps++) len_update_table(which, ps);
 
-    if (avail() == 0) {
-        flush_stream(0);
-        return;
-    }
-    read_match_distances();  // first byte is always a plain literal (:860-878)
-    const uint32_t cur_byte = byte_at(0 - additional_offset);
-    {
+    bool more = avail() != 0;
+    if (more) {
+        // The first byte is always a plain literal (:860-878).  ReadMatchDistances at position 0 finds
+        // nothing (the match finder is empty), so it only advances the window.
+        m = 1;
+        additional_offset = 1;
+        const uint32_t cur_byte = byte_at(0 - additional_offset);
         uint16_t* ptr = model;
         uint32_t bit = 0;
         if (lane == 0) { ptr = p_is_match(state, 0); bit = 0; }
         else if (lane <= 8) literal_decision(lane - 1, lit_coder(0, prev_byte), false, 0, cur_byte, ptr, bit);
-        rc.batch(9, ptr, bit, false);
-    }
-    state = st_lit(state);
-    prev_byte = cur_byte;
-    additional_offset--;
-    now_pos++;
-    if (avail() == 0) {
-        flush_stream(now_pos);
-        return;
+        rc_batch(&ctx->rc, 9, ptr, bit, lane);
+        state = st_lit(state);
+        prev_byte = cur_byte;
+        additional_offset--;
+        now_pos++;
+        more = avail() != 0;
     }
     #pragma unroll 1
-    while (encode_one()) {}
+    while (more) more = encode_one(false);
+    if (eos) encode_one(true);  // Flush (:837-841): the end marker if asked for ...
+    rc_flush(&ctx->rc, lane);   // ... and five shiftLow
 }
 
-__global__ void __launch_bounds__(kEncMaxWarps * 32, 1) lzb_parse_kernel(ParseArgs a) {
+// MAXW = launch bound in warps: the register budget is 64 K / (32 MAXW).  Two instances: up to
+// kEncWarpsLitSmem streams per SM with the literal coders in shared memory (168 registers), and up
+// to kEncMaxWarps with the literal coders in global memory (L2), which is what lets a wave with more
+// blocks than the first variant's slots keep 12-14 serial chains per SM in flight.
+template <int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1) lzb_parse_kernel(ParseArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CtaTables* tables = reinterpret_cast<CtaTables*>(smem_raw);
     init_cta_tables(tables);
@@ -1304,9 +1365,29 @@ __global__ void __launch_bounds__(kEncMaxWarps * 32, 1) lzb_parse_kernel(ParseAr
     uint8_t* slice = smem_raw + sizeof(CtaTables) + (size_t)warp * a.slice_bytes;
     const size_t slot = (size_t)blockIdx.x * warps + warp;
     const ModelLayout L = make_layout(a.lc, a.lp, a.pb);
-    const SliceLayout S = make_slice(a.lc, a.lp, a.pb, a.fb, a.slice_budget);
+    const SliceLayout S = make_slice(a.lc, a.lp, a.pb, a.fb, a.lit_in_smem);
     uint16_t* model = reinterpret_cast<uint16_t*>(slice);
     uint16_t* lit = S.lit_in_smem ? model + L.literal : a.lit_scratch + slot * (size_t)L.n_literal;
+    WarpCtx* ctx = reinterpret_cast<WarpCtx*>(slice + S.ctx);
+    if (lane == 0) {
+        ctx->prob_prices = tables->prob_prices;
+        ctx->fast_pos = tables->fast_pos;
+        ctx->model = model;
+        ctx->dist_prices = reinterpret_cast<uint16_t*>(slice + S.dist_prices);
+        ctx->slot_prices = reinterpret_cast<uint16_t*>(slice + S.slot_prices);
+        ctx->align_prices = reinterpret_cast<uint16_t*>(slice + S.align_prices);
+        ctx->len_prices = reinterpret_cast<uint16_t*>(slice + S.len_prices);
+        ctx->len_counters = reinterpret_cast<int32_t*>(slice + S.len_counters);
+        ctx->pb = a.pb;
+        ctx->table_size = a.fb + 1 - kMatchMinLen;
+        ctx->dist_table_size = a.dist_table_size;
+        ctx->off_len = L.len;
+        ctx->off_rep_len = L.rep_len;
+        ctx->off_pos_slot = L.pos_slot;
+        ctx->off_pos_dec = L.pos_dec;
+        ctx->off_pos_align = L.pos_align;
+    }
+    __syncwarp();
 
     #pragma unroll 1
     for (;;) {
@@ -1349,21 +1430,23 @@ __global__ void __launch_bounds__(kEncMaxWarps * 32, 1) lzb_parse_kernel(ParseAr
             for (uint32_t i = lane; i < words; i += 32) z[i] = 0;
         }
         __syncwarp();
+        rc_init(&ctx->rc, out, cap, lane);
         Enc e;
         e.T = tables;
         e.model = model;
         e.lit = lit;
-        e.dist_prices = reinterpret_cast<uint16_t*>(slice + S.dist_prices);
-        e.slot_prices = reinterpret_cast<uint16_t*>(slice + S.slot_prices);
-        e.align_prices = reinterpret_cast<uint16_t*>(slice + S.align_prices);
-        e.len_prices = reinterpret_cast<uint16_t*>(slice + S.len_prices);
-        e.len_counters = reinterpret_cast<int32_t*>(slice + S.len_counters);
+        e.dist_prices = ctx->dist_prices;
+        e.slot_prices = ctx->slot_prices;
+        e.align_prices = ctx->align_prices;
+        e.len_prices = ctx->len_prices;
+        e.len_counters = ctx->len_counters;
         e.md = reinterpret_cast<uint32_t*>(slice + S.md);
         e.md2 = reinterpret_cast<uint16_t*>(slice + S.md2);
         e.ring = reinterpret_cast<OptNode*>(slice + S.ring);
         e.rsize = S.ring_nodes;
         e.rinv = ((1u << 24) + S.ring_nodes - 1) / S.ring_nodes;
         e.gopt = reinterpret_cast<OptNode*>(a.opt_scratch) + slot * (size_t)kNumOpts;
+        e.ctx = ctx;
         e.L = L;
         e.data = a.mf.in + a.mf.in_off[b];
         e.n = n;
@@ -1380,26 +1463,38 @@ __global__ void __launch_bounds__(kEncMaxWarps * 32, 1) lzb_parse_kernel(ParseAr
         e.pos_mask = (1u << a.pb) - 1;
         e.lp_mask = (1u << a.lp) - 1;
         e.eos = a.eos;
-        e.rc.init(out, cap, lane);
         e.run();
-        if (lane == 0) a.out_len[b] = e.rc.pos > cap ? ~0ull : e.rc.pos + header;
+        if (lane == 0) a.out_len[b] = (uint64_t)ctx->rc.pos > cap ? ~0ull : (uint64_t)ctx->rc.pos + header;
         __syncwarp();
     }
 }
 
 // ---- host side ---------------------------------------------------------------
-ParseGeometry parse_geometry(int lc, int lp, int pb, int fb) {
-    ParseGeometry g;
+// Streams per SM for a wave of `blocks_per_sm` blocks per SM.  With the literal coders in shared
+// memory a stream's slice is 28.5 KB at lc3 lp0 fb 64 (8 per SM); with them in global memory 16.5 KB
+// (13 per SM, the second kernel instance).  A lone stream is 2-3 % faster with shared literals, so the
+// global layout is used only when the wave has more blocks than the shared layout could hold at once
+// (or when the literal coders do not fit shared memory at all: lc + lp > 4).
+ParseGeometry parse_geometry(int lc, int lp, int pb, int fb, uint32_t blocks_per_sm, int force_lit) {
     const uint32_t usable = 232448 - (uint32_t)sizeof(CtaTables);
-    g.slice_budget = usable / 2;  // keep the literal coders in shared memory while two streams still fit an SM
-    const SliceLayout s = make_slice(lc, lp, pb, fb, g.slice_budget);
-    g.slice_bytes = (s.total + 127) & ~127u;
-    int warps = (int)(usable / g.slice_bytes);
-    if (warps > kEncMaxWarps) warps = kEncMaxWarps;
-    if (warps < 1) warps = 1;
-    g.max_warps = warps;
-    g.lit_in_smem = s.lit_in_smem;
-    g.cta_table_bytes = (uint32_t)sizeof(CtaTables);
+    auto geo = [&](bool with_lit) {
+        ParseGeometry g;
+        const SliceLayout s = make_slice(lc, lp, pb, fb, with_lit);
+        g.slice_bytes = (s.total + 127) & ~127u;
+        int warps = (int)(usable / g.slice_bytes);
+        const int cap = with_lit ? kEncWarpsLitSmem : kEncMaxWarps;
+        if (warps > cap) warps = cap;
+        g.max_warps = warps;  // 0: does not fit
+        g.lit_in_smem = with_lit;
+        g.cta_table_bytes = (uint32_t)sizeof(CtaTables);
+        return g;
+    };
+    const ParseGeometry gs = geo(true), gg = geo(false);
+    bool use_smem = gs.max_warps >= 1 && (gs.max_warps >= gg.max_warps || blocks_per_sm <= (uint32_t)gs.max_warps);
+    if (force_lit == 0 && gs.max_warps >= 1) use_smem = true;   // LZB_ENC_LIT=smem  (test / tuning hook)
+    if (force_lit == 1) use_smem = false;                       // LZB_ENC_LIT=global
+    ParseGeometry g = use_smem ? gs : gg;
+    if (g.max_warps < 1) g.max_warps = 1;
     return g;
 }
 
@@ -1407,9 +1502,10 @@ size_t parse_opt_bytes_per_slot() { return sizeof(OptNode) * (size_t)kNumOpts; }
 
 cudaError_t launch_parse(const ParseArgs& a, int grid, int warps, cudaStream_t st) {
     const size_t smem = sizeof(CtaTables) + (size_t)warps * a.slice_bytes;
-    cudaError_t e = cudaFuncSetAttribute(lzb_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    auto kern = a.lit_in_smem ? lzb_parse_kernel<kEncWarpsLitSmem> : lzb_parse_kernel<kEncMaxWarps>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
-    lzb_parse_kernel<<<grid, warps * 32, smem, st>>>(a);
+    kern<<<grid, warps * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -73,6 +73,7 @@ struct EncodeArgs {
     // developer / test hooks, read once when the handle is created (lzb_enc_create)
     int32_t tune_warps = 0;      // LZB_ENC_WARPS: parser streams per SM (0 = automatic)
     int32_t tune_pair_mul = 0;   // LZB_PAIR_MUL: initial match-pair budget in slots per input byte (0 = default)
+    int32_t tune_lit = -1;       // LZB_ENC_LIT: 0 = literal coders in shared memory, 1 = in global memory (-1 = automatic)
     bool tune_fifo = false;      // LZB_ENC_FIFO: plain block order inside a wave
     bool tune_timing = false;    // LZB_ENC_TIMING: phase times of every wave on stderr
 };
@@ -85,7 +86,8 @@ struct EncScratch {
 };
 
 constexpr uint64_t kEncMaxBlockBytes = 1ull << 23;  // match pairs pack len << 23 | distance
-constexpr int kEncMaxWarps = 9;            // upper bound of parser streams resident per SM (shared memory decides, see parse_geometry)
+constexpr int kEncWarpsLitSmem = 9;        // parser streams per SM, literal coders in shared memory (shared memory decides, see parse_geometry)
+constexpr int kEncMaxWarps = 14;           // ... with the literal coders in global memory: 64 K registers / (14 x 32) = 146 per thread
 
 // where the match finder left the lists of the first block of a batch (trace tap)
 struct MfTrace {
