@@ -7,8 +7,7 @@
 #include <new>
 #include <vector>
 
-#include "lzb_common.cuh"
-#include "lzb_kernels.h"
+#include "lzb_encode.cuh"
 #include "lzb_host.h"
 
 using namespace lzbhost;
@@ -114,9 +113,9 @@ int lzb_enc_code_batch_device(lzb_enc* e, const uint8_t* d_in, const uint64_t* d
     if (n == 0) return LZB_OK;
     if (!d_in || !d_in_off || !d_in_len || !d_out || !d_out_off || !d_out_cap || !d_out_len)
         return fail(LZB_E_ARG, "null argument");
-    // match pairs are packed as len << 23 | distance (BinTree.Create itself throws above 2^30 - 257, BinTree.java:95-97)
+    // positions are 32-bit and BinTree.Normalize (BinTree.java:358-375, at 2^30 - 1 positions) is not built
     if (max_in_len > lzb::kEncMaxBlockBytes)
-        return fail(LZB_E_UNSUPPORTED, "block of %llu bytes: the encoder takes blocks of at most %llu bytes",
+        return fail(LZB_E_UNSUPPORTED, "stream of %llu bytes: one stream may have at most %llu bytes",
                     (unsigned long long)max_in_len, (unsigned long long)lzb::kEncMaxBlockBytes);
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
@@ -238,14 +237,19 @@ int lzb_enc_trace_matches(lzb_enc* e, const uint8_t* in, uint64_t in_len, uint32
     add_launches(launches);
     if (err != cudaSuccess) return fail(LZB_E_CUDA, "match finder: %s", cudaGetErrorString(err));
     std::vector<uint32_t> idx, words;
+    std::vector<uint16_t> words2;
     try {
         idx.resize((size_t)in_len + 1);
         words.resize(tr.pair_words ? tr.pair_words : 1);
+        words2.resize(tr.pair_words ? tr.pair_words : 1);
     } catch (...) {
         return fail(LZB_E_NOMEM, "out of host memory");
     }
     CUDA_TRY(cudaMemcpy(idx.data(), tr.idx, idx.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    if (tr.pair_words) CUDA_TRY(cudaMemcpy(words.data(), tr.pairs, (size_t)tr.pair_words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (tr.pair_words) {
+        CUDA_TRY(cudaMemcpy(words.data(), tr.pairs, (size_t)tr.pair_words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(words2.data(), tr.pairs2, (size_t)tr.pair_words * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    }
     uint64_t used = 0;
     for (uint64_t p = 0; p < in_len; p++) {
         const uint32_t off = idx[p + 1];
@@ -254,8 +258,8 @@ int lzb_enc_trace_matches(lzb_enc* e, const uint8_t* in, uint64_t in_len, uint32
         for (uint32_t k = 0; k < cnt; k++, used++) {
             if (used < pairs_cap) {
                 const uint32_t w = words[off + 1 + k];
-                pairs[2 * used] = w >> 23;
-                pairs[2 * used + 1] = w & ((1u << 23) - 1);
+                pairs[2 * used] = lzb::pair_len(w, words2[off + 1 + k]);
+                pairs[2 * used + 1] = lzb::pair_dist(w);
             }
         }
     }

@@ -236,6 +236,7 @@ cudaError_t run_waves(const EncodeArgs& a, const Plan& P, EncScratch& scratch, i
             if (e != cudaSuccess) return e;
             mf_only->idx = w.idx;
             mf_only->pairs = w.pairs;
+            mf_only->pairs2 = w.pairs2;
             mf_only->pair_words = used;
             return cudaSuccess;
         }

@@ -26,9 +26,19 @@ constexpr uint32_t kHash2Size = 1u << 10;
 constexpr uint32_t kHash3Size = 1u << 16;
 constexpr uint32_t kBT2HashSize = 1u << 16;
 constexpr uint32_t kMfEmpty = 0xFFFFFFFFu;  // idx[] value of a position with no pairs
-constexpr int kPairDistBits = 23;            // pair = len << 23 | distance  (blocks <= 8 MiB)
+// A match pair (BinTree.LengthAndDistance, BinTree.java:22-39) is 6 bytes in global memory:
+//   pairs[k]  (u32) = distance | (len & 7) << 29        distance < 2^29 = the largest dictionary (Encoder.java:1135-1146)
+//   pairs2[k] (u16) = cont | (len >> 3) << 9            cont = GetMatchLen after "match + literal" (Encoder.java:769), <= fb <= 273
+// len <= 273 needs 9 bits: the low three ride above the distance, the high six above the continuation.
+constexpr int kPairDistBits = 29;
 constexpr uint32_t kPairDistMask = (1u << kPairDistBits) - 1;
-constexpr uint64_t kEncMaxBlock = 1ull << kPairDistBits;
+__host__ __device__ __forceinline__ uint32_t pair_word(uint32_t len, uint32_t dist) { return dist | ((len & 7u) << kPairDistBits); }
+__host__ __device__ __forceinline__ uint16_t pair2_word(uint32_t len, uint32_t cont) { return (uint16_t)(cont | ((len >> 3) << 9)); }
+__host__ __device__ __forceinline__ uint32_t pair_len(uint32_t w, uint32_t w2) { return (w >> kPairDistBits) | ((w2 >> 9) << 3); }
+__host__ __device__ __forceinline__ uint32_t pair_dist(uint32_t w) { return w & kPairDistMask; }
+__host__ __device__ __forceinline__ uint32_t pair_cont(uint32_t w2) { return w2 & 511u; }
+// Positions are 32-bit and 2 * position + 1 indexes the tree; BinTree.Normalize (2^30 positions) is not built.
+constexpr uint64_t kEncMaxBlock = (1ull << 30) - 1;
 constexpr uint32_t kHeadFlag = 0x80000000u;
 
 // Per-wave scratch; every per-block array is strided by the wave's largest block.
@@ -50,9 +60,9 @@ struct MfWave {
     uint32_t* prev3;         // [n_blocks][np]
     uint32_t* son;           // [n_blocks][2*np]         absolute-indexed tree links
     uint32_t* idx;           // [n_blocks][np]           offset of the position's list in `pairs` or kMfEmpty
-    uint32_t* pairs;         // [n_blocks][pair_cap]     lists: count, then count packed pairs
-    uint16_t* pairs2;        // [n_blocks][pair_cap]     per pair: GetMatchLen(len, dist, fb) after "match + literal"
-                             //                          (Encoder.java:769), a function of the data only
+    uint32_t* pairs;         // [n_blocks][pair_cap]     lists: count, then count pair words (pair_word)
+    uint16_t* pairs2;        // [n_blocks][pair_cap]     per pair: pair2_word -- the rest of the length and the
+                             //                          "match + literal + rep0" continuation, a function of the data only
     uint32_t* pair_used;     // [n_blocks]               zeroed; bump allocator
     uint32_t* overflow;      // [1]                      zeroed; set when a block ran out of pair slots
     uint4* long_items;       // buckets longer than kLongChain: (block, last inserted position, next position, -)

@@ -185,8 +185,18 @@ struct TreeBlock {
 };
 
 // hash-2 / hash-3 candidates (BinTree.java:183-208) or the bt2 direct-byte check (:218-226)
+// A thread's list under construction: distances and lengths side by side (local memory).
+struct PairBuf {
+    uint32_t dist[kMatchMaxLen];
+    uint16_t len[kMatchMaxLen];
+    __device__ __forceinline__ void put(uint32_t i, uint32_t l, uint32_t d) {
+        dist[i] = d;
+        len[i] = (uint16_t)l;
+    }
+};
+
 __device__ __forceinline__ void tree_prepairs(const MfWave& w, const TreeBlock& t, uint32_t pos1, uint32_t cur_match,
-                                              uint32_t match_min_pos, uint32_t* pairs, uint32_t& cnt, uint32_t& max_len) {
+                                              uint32_t match_min_pos, PairBuf& pairs, uint32_t& cnt, uint32_t& max_len) {
     const uint8_t* cur = t.buf + pos1;
     max_len = 1;  // kStartMaxLen
     cnt = 0;
@@ -195,12 +205,12 @@ __device__ __forceinline__ void tree_prepairs(const MfWave& w, const TreeBlock& 
         const uint32_t c3 = t.prev3[pos1];
         if (c2 > match_min_pos && t.buf[c2] == cur[0]) {
             max_len = 2;
-            pairs[cnt++] = (2u << kPairDistBits) | (pos1 - c2 - 1);
+            pairs.put(cnt++, 2, pos1 - c2 - 1);
         }
         if (c3 > match_min_pos && t.buf[c3] == cur[0]) {
             if (c3 == c2) cnt--;
             max_len = 3;
-            pairs[cnt++] = (3u << kPairDistBits) | (pos1 - c3 - 1);
+            pairs.put(cnt++, 3, pos1 - c3 - 1);
             c2 = c3;
         }
         if (cnt != 0 && c2 == cur_match) {
@@ -209,13 +219,13 @@ __device__ __forceinline__ void tree_prepairs(const MfWave& w, const TreeBlock& 
         }
     } else if (cur_match > match_min_pos && t.buf[cur_match + 2] != cur[2]) {
         max_len = 2;
-        pairs[cnt++] = (2u << kPairDistBits) | (pos1 - cur_match - 1);
+        pairs.put(cnt++, 2, pos1 - cur_match - 1);
     }
 }
 
 // write the finished list of a position, with the "match + literal + rep0" continuation of each pair
 // (Encoder.java:766-770 asks for it at every pair boundary; it depends on the data only)
-__device__ __forceinline__ void tree_store_list(const MfWave& w, const TreeBlock& t, uint32_t b, uint32_t pos1, const uint32_t* pairs,
+__device__ __forceinline__ void tree_store_list(const MfWave& w, const TreeBlock& t, uint32_t b, uint32_t pos1, const PairBuf& pairs,
                                                 uint32_t cnt) {
     uint32_t where = kMfEmpty;
     if (cnt) {
@@ -224,14 +234,14 @@ __device__ __forceinline__ void tree_store_list(const MfWave& w, const TreeBlock
             where = off;
             t.pairs_out[off] = cnt;
             for (uint32_t i = 0; i < cnt; i++) {
-                t.pairs_out[off + 1 + i] = pairs[i];
-                const uint32_t len = pairs[i] >> kPairDistBits, dist = pairs[i] & kPairDistMask;
+                const uint32_t len = pairs.len[i], dist = pairs.dist[i];
+                t.pairs_out[off + 1 + i] = pair_word(len, dist);
                 const uint32_t s1 = pos1 + len + 1;  // 1-based start of the continuation
                 uint32_t lim = s1 <= t.n ? t.n + 1 - s1 : 0;
                 if (lim > (uint32_t)w.fb) lim = (uint32_t)w.fb;
                 const uint8_t* a = t.buf + s1;
                 const uint32_t k = lim ? extend_run(a, a - dist - 1, 0, lim, t.n + 1 - s1) : 0;
-                t.pairs2_out[off + 1 + i] = (uint16_t)k;
+                t.pairs2_out[off + 1 + i] = pair2_word(len, k);
             }
         } else {
             atomicMax(w.overflow, 1u);
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__(256) lzb_mf_tree_kernel(MfWave w) {
     uint32_t* son = t.son;
     const uint32_t direct = w.bt4 ? 0 : 2;  // kNumHashDirectBytes
 
-    uint32_t pairs[kMatchMaxLen];
+    PairBuf pairs;
     uint32_t cur_match = 0;  // the hash-4 head: previous position of this bucket (0 = kEmptyHashValue)
     uint32_t done = 0;
     while (pos1 != 0) {
@@ -293,7 +303,7 @@ __global__ void __launch_bounds__(256) lzb_mf_tree_kernel(MfWave w) {
                 len = extend_run(cur, pby1, len + 1, len_limit, remaining);
                 if (max_len < len) {
                     max_len = len;
-                    pairs[cnt++] = (len << kPairDistBits) | (pos1 - cm - 1);
+                    pairs.put(cnt++, len, pos1 - cm - 1);
                     if (len == len_limit) {
                         son[ptr1] = kids.x;
                         son[ptr0] = kids.y;
@@ -330,7 +340,7 @@ constexpr uint32_t kPending = 0xFFFFFFFFu;
 __global__ void __launch_bounds__(256) lzb_mf_long_kernel(MfWave w) {
     const int lane = threadIdx.x & 31;
     const uint32_t direct = w.bt4 ? 0 : 2;
-    uint32_t pairs[kMatchMaxLen];
+    PairBuf pairs;
     for (;;) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(w.long_ticket, 1u);
@@ -395,7 +405,7 @@ __global__ void __launch_bounds__(256) lzb_mf_long_kernel(MfWave w) {
                             have_cmp = false;
                             if (max_len < len) {
                                 max_len = len;
-                                pairs[cnt++] = (len << kPairDistBits) | (pos1 - cm - 1);
+                                pairs.put(cnt++, len, pos1 - cm - 1);
                             }
                             if (full) {
                                 son[ptr1] = kx;

@@ -235,7 +235,7 @@ __host__ __device__ inline SliceLayout make_slice(int lc, int lp, int pb, int fb
     s.len_prices = o;   o += ((2u << pb) * table * 2 + 15) & ~15u;
     s.len_counters = o; o += 32 * 4;
     s.md = o;           o += 288 * 4;
-    s.md2 = o;          o += 288 * 2;
+    s.md2 = o;          o += 288 * 4;
     o = (o + 15) & ~15u;
     s.ring = o;         o += ring_nodes * 32;
     s.total = o;
@@ -380,8 +380,8 @@ struct Enc {
     uint16_t* align_prices; // [16]
     uint16_t* len_prices;   // [2][1<<pb][table_size]
     int32_t* len_counters;  // [2][16]
-    uint32_t* md;           // current match list, len << 23 | distance
-    uint16_t* md2;          // per pair: length of the rep0 continuation after "match + literal"
+    uint32_t* md;           // current match list: distances
+    uint32_t* md2;          // per pair: length | continuation << 16  (continuation = rep0 length after "match + literal")
     OptNode* ring;          // [R] shared
     OptNode* gopt;          // [kNumOpts] global spill
     OptNode* qbase;         // where Backward left the decision queue (ring or gopt)
@@ -478,8 +478,9 @@ struct Enc {
     }
 
     // ---- match list ----
-    __device__ __forceinline__ int md_len(int i) const { return (int)(md[i] >> kPairDistBits); }
-    __device__ __forceinline__ uint32_t md_dist(int i) const { return md[i] & kPairDistMask; }
+    __device__ __forceinline__ int md_len(int i) const { return (int)reinterpret_cast<const uint16_t*>(md2)[2 * i]; }
+    __device__ __forceinline__ int md_cont(int i) const { return (int)reinterpret_cast<const uint16_t*>(md2)[2 * i + 1]; }
+    __device__ __forceinline__ uint32_t md_dist(int i) const { return md[i]; }
 
     // List of 0-based position p: idx[p + 1] -> pairs[off] = count, pairs[off + 1 ..] = pairs.
     // The lists are read one step ahead into registers (lane i holds pair i), and idx[] two steps
@@ -512,13 +513,14 @@ struct Enc {
             if (!consumed && pf_pos == m) {
                 cnt = (int)pf_cnt;
                 if (lane < cnt) {
-                    md[lane] = pf_pair;
-                    md2[lane] = (uint16_t)pf_l2;
+                    md[lane] = pair_dist(pf_pair);
+                    md2[lane] = pair_len(pf_pair, pf_l2) | (pair_cont(pf_l2) << 16);
                 }
 #pragma unroll 1
                 for (int i = 32 + lane; i < cnt; i += 32) {
-                    md[i] = pairs[pf_from + 1 + i];
-                    md2[i] = pairs2[pf_from + 1 + i];
+                    const uint32_t w = pairs[pf_from + 1 + i], w2 = pairs2[pf_from + 1 + i];
+                    md[i] = pair_dist(w);
+                    md2[i] = pair_len(w, w2) | (pair_cont(w2) << 16);
                 }
                 m++;  // fillMatches advanced the window
                 consumed = true;
@@ -1067,7 +1069,7 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
             #pragma unroll 1
             for (num_distance_pairs = 0; new_len > md_len(num_distance_pairs); num_distance_pairs++) {}
             __syncwarp();
-            if (lane == 0) md[num_distance_pairs] = ((uint32_t)new_len << kPairDistBits) | md_dist(num_distance_pairs);
+            if (lane == 0) md2[num_distance_pairs] = (uint32_t)new_len | (md2[num_distance_pairs] & 0xFFFF0000u);  // distance stays
             num_distance_pairs++;
             __syncwarp();
         }
@@ -1081,7 +1083,7 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
                 const int lj = md_len(j);
                 if (lj < start_len || lj >= num_avail_full) continue;
                 const int t = num_avail_full - 1 - lj;
-                int l2 = md2[j];
+                int l2 = md_cont(j);
                 if (l2 > t) l2 = t;
                 if (l2 >= 2 && cur + lj + 1 + l2 > need) need = cur + lj + 1 + l2;
             }
@@ -1148,7 +1150,7 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
                 const int lj = md_len(j);
                 if (lj < start_len || lj >= num_avail_full) continue;
                 const int t = num_avail_full - 1 - lj;
-                int l2 = md2[j];
+                int l2 = md_cont(j);
                 if (l2 > t) l2 = t;
                 if (l2 < 2) continue;
                 const uint32_t cur_back = md_dist(j);
@@ -1441,7 +1443,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) lzb_parse_kernel(ParseArgs a) {
         e.len_prices = ctx->len_prices;
         e.len_counters = ctx->len_counters;
         e.md = reinterpret_cast<uint32_t*>(slice + S.md);
-        e.md2 = reinterpret_cast<uint16_t*>(slice + S.md2);
+        e.md2 = reinterpret_cast<uint32_t*>(slice + S.md2);
         e.ring = reinterpret_cast<OptNode*>(slice + S.ring);
         e.rsize = S.ring_nodes;
         e.rinv = ((1u << 24) + S.ring_nodes - 1) / S.ring_nodes;

@@ -85,14 +85,15 @@ struct EncScratch {
     void release();
 };
 
-constexpr uint64_t kEncMaxBlockBytes = 1ull << 23;  // match pairs pack len << 23 | distance
+constexpr uint64_t kEncMaxBlockBytes = (1ull << 30) - 1;  // one stream; BinTree.Normalize (BinTree.java:358-375) is not built
 constexpr int kEncWarpsLitSmem = 9;        // parser streams per SM, literal coders in shared memory (shared memory decides, see parse_geometry)
 constexpr int kEncMaxWarps = 14;           // ... with the literal coders in global memory: 64 K registers / (14 x 32) = 146 per thread
 
 // where the match finder left the lists of the first block of a batch (trace tap)
 struct MfTrace {
     const uint32_t* idx = nullptr;    // [len + 1], 1-based: offset into pairs or 0xFFFFFFFF
-    const uint32_t* pairs = nullptr;  // count, then count x (len << 23 | distance)
+    const uint32_t* pairs = nullptr;  // count, then count x pair_word (lzb_encode.cuh)
+    const uint16_t* pairs2 = nullptr; // pair2_word per pair
     uint32_t pair_words = 0;          // words in use
 };
 

@@ -178,11 +178,59 @@ def test_encode_8mib_block_max_ratio_settings(lzb, oracle, corpus):
     assert ok and back == data
 
 
-def test_encode_block_larger_than_8mib_is_refused(lzb):
+def _stream_equals_oracle(lzb, oracle, p, data):
+    enc = _encoder(lzb, p)
+    got = enc.code_bytes(data)  # Encoder.Code: payload only
+    enc.close()
+    ref = oracle.encode(data, oracle.props(**p))
+    assert len(got) == len(ref)
+    assert got == ref
+    dec = lzb.Decoder()
+    assert dec.SetDecoderProperties(oracle.props_bytes(oracle.props(**p)))
+    ok, back = dec.code_bytes(got, len(data))
+    dec.close()
+    assert ok and back == bytes(data)
+
+
+def test_encode_stream_longer_than_8mib_and_than_its_dictionary(lzb, oracle, corpus):
+    """Encoder.Code drains any stream to EOF with a sliding window (Encoder.java:1064-1077, InWindow.java:24-63,
+    BinTree.java:84-90,164,231): 12 MiB through a 1 MiB dictionary, twelve window lengths, every class."""
+    p = dict(BASE)
+    data = np.concatenate([corpus.generate(3 << 20, 1, c, 41, c) for c in range(4)])
+    _stream_equals_oracle(lzb, oracle, p, data)
+
+
+def test_encode_lzmabench_buffer_at_d23(lzb, oracle, corpus):
+    """LzmaBench's buffer is dictionary + 2 MiB of its own generator's data (LzmaBench.java:329-332): -d23 = 10 MiB."""
+    p = dict(BASE)
+    p.update(dict_size=1 << 23)
+    data = corpus.generate((1 << 23) + (2 << 20), 1, corpus.REPETITIVE, 42, 0)
+    _stream_equals_oracle(lzb, oracle, p, data)
+
+
+def test_encode_distances_beyond_2_23(lzb, oracle, corpus):
+    """Dictionaries above 8 MiB (SetDictionarySize takes up to 2^29, Encoder.java:1135-1146): the second
+    part of the stream repeats data 9 MiB back, so the chosen matches have distances above 2^23."""
+    p = dict(BASE)
+    p.update(dict_size=1 << 25)
+    a = np.concatenate([corpus.generate(8 << 20, 1, corpus.RANDOM, 43, 0), corpus.generate(1 << 20, 1, corpus.TEXT, 43, 1)])
+    data = np.concatenate([a, a[1 << 20: 7 << 20], a[-(1 << 20):]])
+    _stream_equals_oracle(lzb, oracle, p, data)
+    enc = _encoder(lzb, p)
+    counts, pairs = enc.trace_matches(data[(8 << 20):(8 << 20) + (2 << 20) + 4096])  # the tap speaks the wide format too
+    enc.close()
+    assert counts.sum() == len(pairs)
+
+
+def test_stream_of_2_30_bytes_is_refused(lzb):
+    """The one limit left: a single stream of 2^30 bytes or more (BinTree.Normalize, BinTree.java:358-375, is not built)."""
+    import ctypes as C
     enc = lzb.Encoder()
-    with pytest.raises(lzb.LzbError) as ei:
-        enc.code_bytes(np.zeros((1 << 23) + 1, dtype=np.uint8))
-    assert ei.value.code == lzb.LZB_E_UNSUPPORTED
+    n = C.c_uint64(0)
+    dummy = np.zeros(16, dtype=np.uint8)
+    rc = lzb.lib().lzb_enc_code_batch_device(enc._h, dummy.ctypes.data, dummy.ctypes.data, dummy.ctypes.data, 1, 1 << 30,
+                                             dummy.ctypes.data, dummy.ctypes.data, dummy.ctypes.data, dummy.ctypes.data, 0, None)
+    assert rc == lzb.LZB_E_UNSUPPORTED
     enc.close()
 
 
