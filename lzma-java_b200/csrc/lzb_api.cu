@@ -73,6 +73,7 @@ struct lzb_dec {
     int env_mode = -1;    // LZB_DEC_MODE: 0 = all shared, 1 = hybrid
     int env_chunks = 0;   // LZB_DEC_CHUNKS: 1..16
     int env_marks = 0;    // LZB_DEC_MARKS: 1..32
+    int env_zero_copy = 1;  // LZB_DEC_ZEROCOPY=0: always stage host input through a device copy
 };
 
 namespace {
@@ -93,8 +94,13 @@ void header_scan(const uint8_t* stream, uint64_t len, uint32_t* max_lclp1, uint3
 int pick_dec_mode(uint32_t max_lclp1, uint32_t max_pb1, uint64_t resident, int num_sms, int forced) {
     if (max_lclp1 > 4) return lzb::kDecGlobal;
     if (max_lclp1 == 0) return lzb::kDecSmem;  // no well-formed header: every stream returns 0 at once
-    const lzb::ModelLayout L = lzb::make_layout((int)max_lclp1 - 1, 0, (int)max_pb1 - 1);
-    if ((size_t)(L.n_fixed + L.n_literal) * 2 > lzb::kDecSliceBytes) return lzb::kDecHybrid;  // lc + lp = 3 with pb = 4
+    const int lclp = (int)max_lclp1 - 1;
+    const lzb::ModelLayout L = lzb::make_layout(lclp, 0, (int)max_pb1 - 1);
+    const bool fits_smem = (size_t)(L.n_fixed + L.n_literal) * 2 <= lzb::dec_mode_model(lzb::kDecSmem);
+    const bool fits_hybrid = (size_t)(L.n_fixed + (0x110 << lclp)) * 2 <= lzb::dec_mode_model(lzb::kDecHybrid);
+    if (!fits_smem && !fits_hybrid) return lzb::kDecGlobal;  // lc + lp = 3 with pb = 4
+    if (!fits_smem) return lzb::kDecHybrid;
+    if (!fits_hybrid) return lzb::kDecSmem;
     if (forced == 0) return lzb::kDecSmem;  // test hook
     if (forced == 1) return lzb::kDecHybrid;
     return resident > (uint64_t)num_sms * lzb::kDecMaxWarps ? lzb::kDecHybrid : lzb::kDecSmem;
@@ -103,7 +109,7 @@ int pick_dec_mode(uint32_t max_lclp1, uint32_t max_pb1, uint64_t resident, int n
 // enqueue the decode kernel for n streams (no header scan, no synchronisation)
 int dec_enqueue(lzb_dec* d, const uint8_t* d_in, const uint64_t* d_in_off, const uint64_t* d_in_len, uint32_t n,
                 uint8_t* d_out, const uint64_t* d_out_off, const uint64_t* d_out_cap, uint64_t* d_out_len,
-                int32_t* d_status, uint32_t max_lclp1, int mode, uint32_t* ticket, cudaStream_t st, uint32_t region = 0,
+                int32_t* d_status, uint32_t max_lclp1, uint32_t max_pb1, int mode, uint32_t* ticket, cudaStream_t st, uint32_t region = 0,
                 uint32_t n_regions = 1, uint32_t* progress = nullptr, uint32_t marks = 0, uint32_t mark_step = 0) {
     lzb::DecodeArgs a;
     a.in = d_in;
@@ -174,6 +180,7 @@ lzb_dec* lzb_dec_create(int device) {
     if (const char* e = getenv("LZB_DEC_MODE")) d->env_mode = e[0] == '0' ? 0 : e[0] == '1' ? 1 : -1;
     if (const char* e = getenv("LZB_DEC_CHUNKS")) d->env_chunks = atoi(e);
     if (const char* e = getenv("LZB_DEC_MARKS")) d->env_marks = atoi(e);
+    if (const char* e = getenv("LZB_DEC_ZEROCOPY")) d->env_zero_copy = atoi(e) != 0;
     return d;
 }
 
@@ -229,7 +236,7 @@ int lzb_dec_code_batch_device(lzb_dec* d, const uint8_t* d_in, const uint64_t* d
     CUDA_TRY(cudaMemcpyAsync(scan, ctrl + 1, sizeof scan, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
 
-    return dec_enqueue(d, d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_cap, d_out_len, d_status, scan[0],
+    return dec_enqueue(d, d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_cap, d_out_len, d_status, scan[0], scan[1],
                        pick_dec_mode(scan[0], scan[1], n, d->num_sms, d->env_mode), ctrl, st);
 }
 
@@ -249,7 +256,18 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
     const Span si = span_of(in_off, in_len, n);
     const Span so = span_of(out_off, out_cap, n);
     const size_t in_bytes = si.hi - si.lo, out_bytes = so.hi - so.lo;
-    CUDA_TRY(d->d_in.reserve(in_bytes + 16));
+    // Input in pinned (or registered) host memory is not copied at all: the decoder's input ring is filled by
+    // TMA bulk copies that read the mapped host pages directly, half a ring ahead of the range decoder, so the
+    // kernels start at once instead of after a 300 MB host-to-device copy (12 ms of a 100 ms step on C2).
+    const uint8_t* in_mapped = nullptr;
+    if (d->env_zero_copy && in_bytes) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, in + si.lo) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+            in_mapped = (const uint8_t*)attr.devicePointer;
+        else
+            cudaGetLastError();  // pageable memory: not an error, stage it
+    }
+    if (!in_mapped) CUDA_TRY(d->d_in.reserve(in_bytes + 16));
     CUDA_TRY(d->d_out.reserve(out_bytes + 16));
     // meta: in_off in_len out_off out_cap out_len (u64 x n each) + status (i32 x n)
     const size_t meta_bytes = (size_t)n * (5 * sizeof(uint64_t) + sizeof(int32_t));
@@ -265,7 +283,7 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
         header_scan(in + in_off[i], in_len[i], &max_lclp1, &max_pb1);
     }
     uint64_t* dm = (uint64_t*)d->d_meta.p;
-    uint8_t* d_in = (uint8_t*)d->d_in.p;
+    const uint8_t* d_in = in_mapped ? in_mapped : (const uint8_t*)d->d_in.p;
     uint8_t* d_out = (uint8_t*)d->d_out.p;
 
     // Two ways to keep the PCIe bus busy while the kernels run.
@@ -367,15 +385,16 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
         cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ev_k[c], cudaEventDisableTiming);
         n_events = c + 1;
-        if (cin[c].hi > cin[c].lo)
-            err = cudaMemcpyAsync(d_in + (cin[c].lo - si.lo), in + cin[c].lo, cin[c].hi - cin[c].lo, cudaMemcpyHostToDevice, d->copy_in);
+        if (!in_mapped && cin[c].hi > cin[c].lo)
+            err = cudaMemcpyAsync((uint8_t*)d->d_in.p + (cin[c].lo - si.lo), in + cin[c].lo, cin[c].hi - cin[c].lo, cudaMemcpyHostToDevice,
+                                  d->copy_in);
         if (err != cudaSuccess) break;
         cudaEventRecord(ev_in[c], d->copy_in);
         cudaStream_t ks = d->kstream[c % n_k];
         cudaStreamWaitEvent(ks, ready, 0);
         cudaStreamWaitEvent(ks, ev_in[c], 0);
         rc = dec_enqueue(d, d_in, dm + s0, dm + n + s0, cnt, d_out, dm + 2 * (size_t)n + s0, dm + 3 * (size_t)n + s0,
-                         dm + 4 * (size_t)n + s0, (int32_t*)(dm + 5 * (size_t)n) + s0, max_lclp1, mode,
+                         dm + 4 * (size_t)n + s0, (int32_t*)(dm + 5 * (size_t)n) + s0, max_lclp1, max_pb1, mode,
                          (uint32_t*)d->ctrl.p + c, ks, c % n_k, n_k, rows[c].on ? (uint32_t*)d->h_progress.p + c * kMarks : nullptr,
                          rows[c].marks, rows[c].step);
         if (rc != LZB_OK) break;

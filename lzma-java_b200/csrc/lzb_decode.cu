@@ -27,58 +27,174 @@ namespace lzb {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
+// ---- compressed input: a per-warp shared-memory ring filled by TMA bulk copies -------------------
+// The reference reads its input one byte per normalisation (RangeDecoder.java:23,36,50,59).  Here a
+// stream's compressed bytes are staged through a small ring in shared memory: lane 0 issues
+// cp.async.bulk (the TMA unit's 1-D copy, UBLKCP in SASS) a quarter of the ring at a time, completion
+// is counted on one mbarrier per quarter, and normalize() takes its byte with one LDS from an address
+// that is a single LOP3 away from the read position (the ring is aligned to its size).
+// The ring is checked once per SYMBOL, not per byte: a symbol consumes at most 48 bytes (a match with
+// 26 direct bits), a quarter is at least 64 bytes, and at every symbol start the quarter under the
+// read position and the two after it have landed while the fourth is in flight.  So the bit decoder
+// itself carries no bounds test at all: past the end of the payload the ring simply holds 0xFF, which
+// is what the reference's InputStream.read() = -1 ORs into the code (RangeDecoder.java:23,36).
+// A quarter lasts a stream ~100 us, which hides HBM latency -- and PCIe latency too: the source may be
+// pinned HOST memory, so a host-buffer batch needs no input copy before the launch.
+// Ring position `rp` counts bytes from g0, the 16-byte-aligned address at or below the payload start.
+struct __align__(16) InRing {
+    uint64_t mbar[4];   // one per quarter
+    uint64_t g0;        // global address of ring position 0 (16-byte aligned)
+    uint32_t end_rp;    // ring position of the first byte past the payload
+    uint32_t total;     // bytes to fetch from g0 on (a multiple of 16)
+    uint32_t state;     // bits 0-3: phase parity of mbar[q]; bits 4-7: a copy into quarter q is pending
+    uint32_t pad[3];
+};
+static_assert(sizeof(InRing) == 64, "InRing header");
+constexpr uint32_t kInRingHeader = (uint32_t)sizeof(InRing);
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar_s) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar_s, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_LOOP;\n\t"
+        "}" ::"r"(mbar_s), "r"(parity) : "memory");
+}
+// one TMA bulk copy global -> shared of `bytes` (a multiple of 16), completion counted on the mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_s, uint64_t src_g, uint32_t bytes, uint32_t mbar_s) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses of this quarter precede the async write
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_s), "l"(src_g), "r"(bytes), "r"(mbar_s) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// Request absolute chunk `c` of the stream (ring positions [c * chunk, (c + 1) * chunk)) into its
+// quarter, or fill the quarter with 0xFF when the payload ends before it.
+__device__ __forceinline__ void ring_request(uint32_t hdr_s, uint32_t ring_s, uint32_t chunk, uint32_t c) {
+    const uint32_t q = c & 3u, from = c * chunk, total = lds_u32(hdr_s + 44);
+    const uint32_t dst = ring_s + q * chunk;
+    if (from < total) {
+        uint32_t bytes = total - from;
+        if (bytes > chunk) bytes = chunk;
+        uint64_t g0;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(g0) : "r"(hdr_s + 32) : "memory");
+        bulk_copy_g2s(dst, g0 + from, bytes, hdr_s + 8 * q);
+        sts_u32(hdr_s + 48, lds_u32(hdr_s + 48) | (16u << q));
+    } else {
+#pragma unroll 1
+        for (uint32_t i = 0; i < chunk; i += 4) sts_u32(dst + i, 0xFFFFFFFFu);
+    }
+}
+// Make absolute chunk `c` readable: wait for its copy, then blank whatever follows the payload inside it.
+__device__ __forceinline__ void ring_land(uint32_t hdr_s, uint32_t ring_s, uint32_t chunk, uint32_t c) {
+    const uint32_t q = c & 3u, st = lds_u32(hdr_s + 48);
+    if (!(st & (16u << q))) return;  // nothing pending: landed earlier, or a 0xFF quarter
+    mbar_wait(hdr_s + 8 * q, (st >> q) & 1u);
+    sts_u32(hdr_s + 48, (st ^ (1u << q)) & ~(16u << q));
+    const uint32_t end_rp = lds_u32(hdr_s + 40), lo = c * chunk, hi = lo + chunk;
+    if (end_rp < hi) {
+#pragma unroll 1
+        for (uint32_t i = end_rp > lo ? end_rp : lo; i < hi; i++) sts_u8(ring_s + q * chunk + (i - lo), 0xFFu);
+    }
+}
+// The read position crossed into absolute chunk c = rp / chunk (checked at symbol starts): chunk c - 1 is
+// used up, so its quarter takes chunk c + 3, and chunk c + 2 must have landed before the next symbol.
+// Once per 64-256 compressed bytes.  Returns the next position to call it at.
+template <uint32_t RING>
+__device__ __forceinline__ uint32_t ring_advance(uint32_t hdr_s, uint32_t ring_s, uint32_t rp) {
+    constexpr uint32_t chunk = RING / 4;
+    const uint32_t c = rp / chunk;
+    ring_request(hdr_s, ring_s, chunk, c + 3);
+    ring_land(hdr_s, ring_s, chunk, c + 2);
+    return (c + 1) * chunk;
+}
+
 // Range decoder state of one stream, in lane 0's registers.  With 28 streams per
 // SM the kernel is issue-bound (profiles/r01_decode_hybrid_ncu.txt: 85 % of issue
 // slots busy), so what matters is the instruction count of a bit decode.  `bit_s`
 // is written in PTX against a shared-memory byte address: 12 instructions
 // (LDS, SHF, IMAD, ISETP, IADD, SEL, @IADD, SEL, IMAD, SHF, STS, SEL).
+template <uint32_t RING>
 struct RangeDec {
-    uint32_t range, code, nextb, ip, len;
-    const uint8_t* in;
+    uint32_t range, code, nextb, beyond, rp, check, end_rp;
+    uint32_t ring_s, hdr_s;  // shared addresses of the ring (aligned to RING) and of its header
 
-    // InputStream.read(): bytes past the end read as -1, which the reference
-    // ORs into _code as all ones (RangeDecoder.java:23,36).
+    // InputStream.read(): past the end of the payload it returns -1, which the reference ORs into _code as
+    // all ones (RangeDecoder.java:23,36) -- so such a "byte" is 0xFFFFFFFF here, not 0xFF.
     __device__ __forceinline__ void fetch() {
-        nextb = 0xFFFFFFFFu;
-        if (ip < len) nextb = __ldg(in + ip);
-        ip++;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(nextb) : "r"(ring_s | (rp & (RING - 1))) : "memory");
+        beyond = rp < end_rp ? 0u : 0xFFFFFFFFu;  // ORed in with the byte; kept apart so that nothing waits for the load
+        rp++;
     }
-    __device__ __forceinline__ void init(const uint8_t* p, uint32_t n) {  // RangeDecoder.java:19-25
-        in = p;
-        len = n;
-        ip = 0;
+    // the reader crossed into the next quarter (seen at a symbol start, Decoder.Code's loop head)
+    __device__ __forceinline__ void advance() { check = ring_advance<RING>(hdr_s, ring_s, rp); }
+    // RangeDecoder.java:19-25.  `p` / `n`: the payload; the mbarriers of the header at `hdr` were
+    // initialised once per warp and carry their phase from stream to stream.
+    __device__ __forceinline__ void init(const uint8_t* p, uint32_t n, uint32_t hdr, uint32_t ring) {
+        constexpr uint32_t chunk = RING / 4;
+        hdr_s = hdr;
+        ring_s = ring;
+        const uint64_t addr = reinterpret_cast<uint64_t>(p);
+        const uint32_t skew = (uint32_t)(addr & 15u);
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(hdr_s + 32), "l"(addr - skew) : "memory");
+        end_rp = skew + n;
+        sts_u32(hdr_s + 40, end_rp);
+        sts_u32(hdr_s + 44, (end_rp + 15u) & ~15u);
+#pragma unroll 1
+        for (uint32_t c = 0; c < 4; c++) ring_request(hdr_s, ring_s, chunk, c);
+#pragma unroll 1
+        for (uint32_t c = 0; c < 3; c++) ring_land(hdr_s, ring_s, chunk, c);
+        rp = skew;
+        check = chunk;
         code = 0;
         range = 0xFFFFFFFFu;
         fetch();
 #pragma unroll 1
         for (int i = 0; i < 5; i++) {
-            code = (code << 8) | nextb;
+            code = (code << 8) | nextb | beyond;
             fetch();
         }
     }
-    // RangeDecoder.java:33-37,58-62.  Only lane 0 runs the range decoder, so the branch
-    // cannot diverge: `bra.uni` tells ptxas, which then drops the BSSY/BSYNC pair it
-    // would otherwise wrap around every normalisation (2 of 20 instructions per bit).
+    // the stream is over: no copy may still be in flight when the next stream reuses the ring
+    __device__ __forceinline__ void drain() {
+        const uint32_t c = rp / (RING / 4);
+#pragma unroll 1
+        for (uint32_t k = 0; k < 4; k++) ring_land(hdr_s, ring_s, RING / 4, c + k);
+    }
+    // RangeDecoder.java:33-37,58-62.  A real branch around the refill, in PTX: left to itself the compiler
+    // predicates these eight instructions, and predicated-off instructions still take issue slots in a
+    // kernel whose only active lane is issue-bound (measured: 85 -> 102 ms per C2 pass).
     __device__ __forceinline__ void normalize() {
         asm volatile(
             "{\n\t"
             ".reg .pred q, h;\n\t"
-            ".reg .u64 ad;\n\t"
+            ".reg .u32 t;\n\t"
             "setp.gt.u32 q, %0, 0xFFFFFF;\n\t"
             "@q bra.uni NORM_DONE;\n\t"
             "shl.b32 %0, %0, 8;\n\t"
             "shl.b32 %1, %1, 8;\n\t"
-            "or.b32 %1, %1, %2;\n\t"
-            "setp.lt.u32 h, %3, %4;\n\t"
-            "cvt.u64.u32 ad, %3;\n\t"
-            "add.u64 ad, ad, %5;\n\t"
-            "mov.u32 %2, 0xFFFFFFFF;\n\t"
-            "@h ld.global.nc.u8 %2, [ad];\n\t"
+            "lop3.b32 %1, %1, %2, %4, 0xFE;\n\t"
+            "and.b32 t, %3, %7;\n\t"
+            "or.b32 t, t, %5;\n\t"
+            "ld.shared.u8 %2, [t];\n\t"
+            "setp.ge.u32 h, %3, %6;\n\t"
+            "selp.u32 %4, 0xFFFFFFFF, 0, h;\n\t"
             "add.u32 %3, %3, 1;\n\t"
             "NORM_DONE:\n\t"
             "}"
-            : "+r"(range), "+r"(code), "+r"(nextb), "+r"(ip)
-            : "r"(len), "l"(in)
+            : "+r"(range), "+r"(code), "+r"(nextb), "+r"(rp), "+r"(beyond)
+            : "r"(ring_s), "r"(end_rp), "n"(RING - 1)
             : "memory");
     }
     // RangeDecoder.DecodeBit (:43-64) on a shared-memory probability, branch-free:
@@ -237,14 +353,16 @@ struct RangeDec {
 };
 
 // LenDecoder.Decode (Decoder.java:48-59) on the pb-strided layout; `slen` = shared address of the coder
-__device__ __forceinline__ uint32_t decode_len(RangeDec& rd, uint32_t slen, int pb, uint32_t pos_state) {
+template <class RD>
+__device__ __forceinline__ uint32_t decode_len(RD& rd, uint32_t slen, int pb, uint32_t pos_state) {
     if (rd.bit_s(slen) == 0) return rd.tree<kNumLowLenBits>(slen + 2 * len_low(pb, pos_state));
     if (rd.bit_s(slen + 2) == 0) return kNumLowLenSymbols + rd.tree<kNumMidLenBits>(slen + 2 * len_mid(pb, pos_state));
     return kNumLowLenSymbols + kNumMidLenSymbols + rd.tree_n(slen + 2 * len_high(pb), kNumHighLenBits);
 }
 
 // LiteralDecoder.Decoder2.DecodeNormal (Decoder.java:70-77), unrolled
-__device__ __forceinline__ uint32_t decode_literal_s(RangeDec& rd, uint32_t sprobs) {
+template <class RD>
+__device__ __forceinline__ uint32_t decode_literal_s(RD& rd, uint32_t sprobs) {
     uint32_t a = sprobs + 2;
     const uint32_t nsb = 0u - sprobs;
 #pragma unroll
@@ -253,7 +371,8 @@ __device__ __forceinline__ uint32_t decode_literal_s(RangeDec& rd, uint32_t spro
 }
 // DecodeWithMatchByte (Decoder.java:79-95): `offs` is 0x100 while the decoded bits still agree
 // with the match byte (probability index ((1 + matchBit) << 8) + symbol), 0 afterwards.
-__device__ __forceinline__ uint32_t decode_literal_matched_s(RangeDec& rd, uint32_t sprobs, uint32_t match_byte) {
+template <class RD>
+__device__ __forceinline__ uint32_t decode_literal_matched_s(RD& rd, uint32_t sprobs, uint32_t match_byte) {
     uint32_t symbol = 1, offs = 0x100u;
 #pragma unroll 1
     do {
@@ -271,7 +390,8 @@ __device__ __forceinline__ uint32_t decode_literal_matched_s(RangeDec& rd, uint3
 // literals part from their match byte within a few bits, so the top three levels of the matched
 // trees (symbol < 8: 16 slots per coder at `stop`, index (matchBit << 3) + symbol) stay in shared
 // memory as well and only the deeper, rarer nodes cost an L2 round trip.
-__device__ __forceinline__ uint32_t decode_literal_matched_h(RangeDec& rd, uint32_t sprobs, uint32_t stop, uint16_t* gprobs,
+template <class RD>
+__device__ __forceinline__ uint32_t decode_literal_matched_h(RD& rd, uint32_t sprobs, uint32_t stop, uint16_t* gprobs,
                                                              uint32_t match_byte) {
     uint32_t symbol = 1;
 #pragma unroll 1
@@ -287,7 +407,8 @@ __device__ __forceinline__ uint32_t decode_literal_matched_h(RangeDec& rd, uint3
     return symbol & 0xFF;
 }
 // both forms on a generic pointer
-__device__ __forceinline__ uint32_t decode_literal_g(RangeDec& rd, uint16_t* probs, bool matched, uint32_t match_byte) {
+template <class RD>
+__device__ __forceinline__ uint32_t decode_literal_g(RD& rd, uint16_t* probs, bool matched, uint32_t match_byte) {
     uint32_t symbol = 1, offs = matched ? 0x100u : 0u;
 #pragma unroll 1
     do {
@@ -312,7 +433,7 @@ __device__ __forceinline__ void report_progress(const DecodeArgs& a, uint32_t fr
 }
 
 template <int MODE, bool PROGRESS>
-__device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, uint16_t* lit_global, int lane) {
+__device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, uint16_t* lit_global, uint32_t hdr_s, uint32_t ring_s, int lane) {
     const uint64_t in_len = a.in_len[s];
     const uint8_t* in = a.in + a.in_off[s];
     uint8_t* out = a.out + a.out_off[s];
@@ -342,7 +463,7 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
         const int n_lit_g = MODE == kDecSmem ? 0 : MODE == kDecHybrid ? 0x200 << (lc + lp) : L.n_literal;
         if (pb > 4 || (int32_t)dict < 0) {
             status = 0;
-        } else if ((size_t)(L.n_fixed + n_lit_s) * 2 > dec_mode_slice(MODE) || (MODE != kDecSmem && (size_t)n_lit_g > a.lit_stride)) {
+        } else if ((size_t)(L.n_fixed + n_lit_s) * 2 > dec_mode_model(MODE) || (MODE != kDecSmem && (size_t)n_lit_g > a.lit_stride)) {
             status = LZB_KERNEL_E_UNSUPPORTED;  // the host picked a mode this stream's lc/lp/pb does not fit
         } else {
             for (int i = lane; i < L.n_fixed + n_lit_s; i += 32) model[i] = kProbInit;  // Decoder.Init :184-203
@@ -354,7 +475,7 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
             // outSize < 0 decodes until the end marker; a size beyond the capacity ends in EV_CAPACITY
             const uint32_t limit = usize > (uint64_t)cap ? 0xFFFFFFFFu : (uint32_t)usize;
 
-            RangeDec rd;
+            RangeDec<dec_mode_ring(MODE)> rd;
             const uint32_t sm = (uint32_t)__cvta_generic_to_shared(model);  // shared byte address of the model
             int state = 0;
             uint32_t rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0;
@@ -362,7 +483,7 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
             uint32_t pend_b = 0;  // deferred tail of the last match copy (one byte per lane)
             uint8_t* pend_dst = out;
             bool pend_valid = false;
-            if (lane == 0) rd.init(in + LZB_KERNEL_HEADER, (uint32_t)(in_len - LZB_KERNEL_HEADER));
+            if (lane == 0) rd.init(in + LZB_KERNEL_HEADER, (uint32_t)(in_len - LZB_KERNEL_HEADER), hdr_s, ring_s);
 
             for (;;) {
                 uint32_t evlen = EV_DONE;  // event | len << 2
@@ -371,6 +492,9 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
                     uint32_t len = 0;
 #pragma unroll 1
                     while (pos < limit) {  // Decoder.Code :219
+                        // the one place the input ring is looked after, once per symbol: leave the symbol loop with
+                        // the "refill" event (a match of length 0) so that no call sits inside it
+                        if (rd.rp >= rd.check) { ev = EV_MATCH; len = 0; break; }
                         const uint32_t pos_state = pos & pos_mask;
                         if (rd.bit_s(sm + 2 * (L.is_match + (state << pb) + pos_state)) == 0) {
                             const uint32_t ctx = ((pos & lp_mask) << lc) + (prev_byte >> (8 - lc));
@@ -455,6 +579,11 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
                 // the tail of the previous match is still in registers: store it now that its loads
                 // have landed (lane 0 decoded a whole symbol under their L2 latency)
                 if (pend_valid) *pend_dst = (uint8_t)pend_b;
+                pend_valid = false;
+                if (evlen == 0) {  // refill event: the read position crossed into the next quarter of the input ring
+                    if (lane == 0) rd.advance();
+                    continue;
+                }
                 const int ev = (int)(evlen & 3);
                 if (ev != EV_MATCH) {
                     status = ev == EV_DONE ? 1 : (ev == EV_DATA_ERROR ? 0 : LZB_KERNEL_E_CAPACITY);
@@ -498,6 +627,7 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
                 pend_dst = dst + k;
                 pos += len;
             }
+            if (lane == 0) rd.drain();  // no input copy may be in flight when the next stream takes the ring
         }
     }
     if (lane == 0) {
@@ -509,16 +639,28 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
 
 template <int MODE, bool PROGRESS>
 __global__ void __launch_bounds__(dec_mode_warps(MODE) * 32, 1) lzb_decode_kernel(DecodeArgs a) {
-    extern __shared__ __align__(16) uint16_t smem[];
+    // dynamic shared memory: [input rings, one per warp, each aligned to its size][ring headers][model slices]
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr uint32_t RING = dec_mode_ring(MODE);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint16_t* model = smem + (size_t)warp * (dec_mode_slice(MODE) / 2);
+    const uint32_t warps = blockDim.x >> 5;
+    const uint32_t base_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t ring_s = base_s + (uint32_t)warp * RING;
+    const uint32_t hdr_s = base_s + warps * RING + (uint32_t)warp * kInRingHeader;
+    uint16_t* model = reinterpret_cast<uint16_t*>(smem_raw + warps * (RING + kInRingHeader) + (size_t)warp * dec_mode_model(MODE));
+    if (lane == 0) {  // the input ring's mbarriers, once per warp (InRing)
+        for (uint32_t q = 0; q < 4; q++) mbar_init(hdr_s + 8 * q);
+        sts_u32(hdr_s + 48, 0);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     uint16_t* lit_global = MODE == kDecSmem ? nullptr
                                             : a.lit_scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * a.lit_stride;
     // first stream by position (warp-major, so a small batch spreads over all SMs), then by ticket
     const uint32_t slots = gridDim.x * (blockDim.x >> 5);
     uint32_t s = (uint32_t)warp * gridDim.x + blockIdx.x;
     while (s < a.n) {
-        decode_stream<MODE, PROGRESS>(a, s, model, lit_global, lane);
+        decode_stream<MODE, PROGRESS>(a, s, model, lit_global, hdr_s, ring_s, lane);
         if (lane == 0) s = slots + atomicAdd(a.ticket, 1u);
         s = __shfl_sync(kFull, s, 0);
     }

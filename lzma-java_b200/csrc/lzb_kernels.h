@@ -23,11 +23,16 @@ enum DecMode : int {
     kDecGlobal = 2,  // all literal tables in global memory (any lc, lp)
 };
 constexpr int kDecMaxWarps = 15;          // streams resident per SM, kDecSmem / kDecGlobal
-constexpr size_t kDecSliceBytes = 15488;  // 15 * 15488 = 232 320 B <= 227 KB per CTA
 constexpr int kDecHybridWarps = 28;       // 28 warps * 72 registers fill the register file
-constexpr size_t kDecHybridSlice = 8064;  // fixed part (pb = 4: 3696 B) + 8 normal literal trees (4096 B) + top of the matched trees (256 B)
+// Shared memory of one stream = its model slice + the input ring (a power of two, aligned to its size) + the ring's
+// 64-byte header.  Model slices: the whole lc + lp = 3 model up to pb = 3 (15 088 B); in the hybrid mode the fixed part
+// (pb = 3: 2800 B) + 8 normal literal trees (4096 B) + the top of the matched trees (256 B); fixed part only (pb = 4: 3696 B).
+constexpr size_t kDecRingHeader = 64;
+__host__ __device__ constexpr size_t dec_mode_model(int mode) { return mode == kDecSmem ? 15088 : mode == kDecHybrid ? 7152 : 3696; }
+__host__ __device__ constexpr uint32_t dec_mode_ring(int mode) { return mode == kDecSmem ? 256u : mode == kDecHybrid ? 512u : 1024u; }
 __host__ __device__ constexpr int dec_mode_warps(int mode) { return mode == kDecHybrid ? kDecHybridWarps : kDecMaxWarps; }
-__host__ __device__ constexpr size_t dec_mode_slice(int mode) { return mode == kDecHybrid ? kDecHybridSlice : kDecSliceBytes; }
+__host__ __device__ constexpr size_t dec_mode_slice(int mode) { return dec_mode_model(mode) + kDecRingHeader + dec_mode_ring(mode); }
+static_assert(kDecMaxWarps * dec_mode_slice(kDecSmem) <= 232448 && kDecHybridWarps * dec_mode_slice(kDecHybrid) <= 232448, "227 KB per CTA");
 
 struct DecodeArgs {
     const uint8_t* in;
