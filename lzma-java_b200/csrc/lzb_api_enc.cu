@@ -26,7 +26,8 @@ struct lzb_enc {
     DevBuf d_in, d_out, d_meta;
     PinBuf h_meta;
     // developer / test hooks (DESIGN.md "test hooks"), read ONCE when the handle is created
-    int32_t tune_warps = 0, tune_pair_mul = 0, tune_lit = -1;
+    int32_t tune_warps = 0, tune_pair_mul = 0, tune_lit = -1, tune_group = 0;
+    int64_t tune_pool = 0;
     bool tune_fifo = false, tune_timing = false;
 };
 
@@ -46,6 +47,8 @@ lzb_enc* lzb_enc_create(int device) {
     if (const char* v = getenv("LZB_ENC_WARPS")) e->tune_warps = atoi(v) > 0 ? atoi(v) : 0;
     if (const char* v = getenv("LZB_PAIR_MUL")) e->tune_pair_mul = atoi(v) > 0 ? atoi(v) : 0;
     if (const char* v = getenv("LZB_ENC_LIT")) e->tune_lit = v[0] == 's' ? 0 : v[0] == 'g' ? 1 : -1;  // smem / global
+    if (const char* v = getenv("LZB_ENC_GROUP")) e->tune_group = atoi(v) > 0 ? atoi(v) : 0;
+    if (const char* v = getenv("LZB_ENC_POOL_MB")) e->tune_pool = atoll(v) > 0 ? atoll(v) << 20 : 0;
     e->tune_fifo = getenv("LZB_ENC_FIFO") != nullptr;
     e->tune_timing = getenv("LZB_ENC_TIMING") != nullptr;
     return e;
@@ -140,6 +143,8 @@ int lzb_enc_code_batch_device(lzb_enc* e, const uint8_t* d_in, const uint64_t* d
     a.tune_warps = e->tune_warps;
     a.tune_pair_mul = e->tune_pair_mul;
     a.tune_lit = e->tune_lit;
+    a.tune_group = e->tune_group;
+    a.tune_pool = e->tune_pool;
     a.tune_fifo = e->tune_fifo;
     a.tune_timing = e->tune_timing;
     int launches = 0;

@@ -41,7 +41,10 @@ __host__ __device__ __forceinline__ uint32_t pair_cont(uint32_t w2) { return w2 
 constexpr uint64_t kEncMaxBlock = (1ull << 30) - 1;
 constexpr uint32_t kHeadFlag = 0x80000000u;
 
-// Per-wave scratch; every per-block array is strided by the wave's largest block.
+// Scratch of one match-finder GROUP of blocks; every per-block array is strided by the group's largest block.
+// The lists it produces are temporary (bump-allocated in the order the tree threads finish); lzb_list_* then
+// compacts them, position-ordered and exactly sized, into the wave's list pool (BlockLists) and this scratch
+// is reused by the next group.
 struct MfWave {
     const uint8_t* in;
     const uint64_t* in_off;  // already offset to the wave's first block
@@ -60,6 +63,7 @@ struct MfWave {
     uint32_t* prev3;         // [n_blocks][np]
     uint32_t* son;           // [n_blocks][2*np]         absolute-indexed tree links
     uint32_t* idx;           // [n_blocks][np]           offset of the position's list in `pairs` or kMfEmpty
+    uint16_t* cnt;           // [n_blocks][np]           number of pairs of the position (0: no list)
     uint32_t* pairs;         // [n_blocks][pair_cap]     lists: count, then count pair words (pair_word)
     uint16_t* pairs2;        // [n_blocks][pair_cap]     per pair: pair2_word -- the rest of the length and the
                              //                          "match + literal + rep0" continuation, a function of the data only
@@ -71,8 +75,23 @@ struct MfWave {
 };
 constexpr uint32_t kLongChain = 48;  // positions a bucket's thread inserts itself before handing over
 
+// Where the lists of one block live in the wave's list pool (byte offsets): idx[n + 1] (1-based: offset of the
+// position's list in `pairs`, or kMfEmpty), then the lists in POSITION ORDER -- count, then count pair words --
+// and the parallel pair2 halfwords.  Consecutive positions are neighbours in memory, so the parser's reads of a
+// block walk forward through three arrays instead of hopping between sectors.
+struct BlockLists {
+    uint64_t idx_off, pairs_off, pairs2_off;
+};
+constexpr uint32_t kListTile = 2048;   // positions per CTA of the compaction kernels (256 threads x 8)
+constexpr uint32_t kListSlack = 64;    // pair slots after a block's lists: the parser prefetches 32 slots blindly
+
 struct ParseArgs {
-    MfWave mf;               // inputs + match lists of the wave
+    const uint8_t* in;       // inputs of the wave
+    const uint64_t* in_off;  // already offset to the wave's first block
+    const uint64_t* in_len;
+    uint32_t n_blocks;
+    const uint8_t* pool;     // list pool of the wave
+    const BlockLists* lists; // [n_blocks]
     uint8_t* out;
     const uint64_t* out_off; // already offset to the wave's first block
     const uint64_t* out_cap;
@@ -96,6 +115,11 @@ struct ParseGeometry {
 
 cudaError_t upload_mf_tables();
 cudaError_t launch_mf(const MfWave& w, uint32_t max_len, int num_sms, cudaStream_t st, cudaEvent_t* ev = nullptr);
+// list compaction: per-tile sizes + per-block scan (tile_sum becomes the exclusive tile offsets, w_total[b] the
+// block's pair words), then the gather into the pool once the host has placed the blocks
+cudaError_t launch_list_scan(const MfWave& w, uint32_t max_len, uint32_t* tile_sum, uint32_t* w_total, cudaStream_t st);
+cudaError_t launch_list_gather(const MfWave& w, uint32_t max_len, const uint32_t* tile_off, const BlockLists* lists, uint8_t* pool,
+                               cudaStream_t st);
 cudaError_t launch_parse(const ParseArgs& a, int grid, int warps, cudaStream_t st);
 ParseGeometry parse_geometry(int lc, int lp, int pb, int fb, uint32_t blocks_per_sm, int force_lit);
 size_t parse_opt_bytes_per_slot();

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(128) lzb_mf_link_kernel(MfWave w) {
     uint32_t* prev2 = w.prev2 + (size_t)b * w.np;
     uint32_t* prev3 = w.prev3 + (size_t)b * w.np;
     uint32_t* idx = w.idx + (size_t)b * w.np;
+    uint16_t* cnt_out = w.cnt + (size_t)b * w.np;
     uint32_t* head3 = heads + kHash2Size;
     uint32_t* head4 = w.bt4 ? heads + kHash2Size + kHash3Size : heads;  // kFixHashSize, BinTree.java:57-69
     const uint32_t min_check = w.bt4 ? 4 : 3;                           // kMinMatchCheck
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(128) lzb_mf_link_kernel(MfWave w) {
             prev3[pos1] = c3;
         } else if (in_range) {
             idx[pos1] = kMfEmpty;
+            cnt_out[pos1] = 0;
             prev2[pos1] = 0;
         }
         __syncwarp();
@@ -168,6 +170,7 @@ struct TreeBlock {
     const uint32_t* next;
     uint32_t* son;
     uint32_t* idx;
+    uint16_t* cnt;
     uint32_t* pairs_out;
     uint16_t* pairs2_out;
     uint32_t n;
@@ -178,6 +181,7 @@ struct TreeBlock {
         next = w.next + (size_t)b * w.np;
         son = w.son + (size_t)b * 2 * w.np;
         idx = w.idx + (size_t)b * w.np;
+        cnt = w.cnt + (size_t)b * w.np;
         pairs_out = w.pairs + (size_t)b * w.pair_cap;
         pairs2_out = w.pairs2 + (size_t)b * w.pair_cap;
         n = (uint32_t)w.in_len[b];
@@ -223,8 +227,10 @@ __device__ __forceinline__ void tree_prepairs(const MfWave& w, const TreeBlock& 
     }
 }
 
-// write the finished list of a position, with the "match + literal + rep0" continuation of each pair
-// (Encoder.java:766-770 asks for it at every pair boundary; it depends on the data only)
+// write the finished list of a position into the block's temporary area (bump-allocated).  The second half
+// of a pair word, the "match + literal + rep0" continuation (Encoder.java:766-770), is filled in by the
+// compaction pass (lzb_list_gather): it is a function of the data only, costs a memory round trip per pair,
+// and a bucket's insertions are a serial chain that must not wait for it.
 __device__ __forceinline__ void tree_store_list(const MfWave& w, const TreeBlock& t, uint32_t b, uint32_t pos1, const PairBuf& pairs,
                                                 uint32_t cnt) {
     uint32_t where = kMfEmpty;
@@ -234,20 +240,27 @@ __device__ __forceinline__ void tree_store_list(const MfWave& w, const TreeBlock
             where = off;
             t.pairs_out[off] = cnt;
             for (uint32_t i = 0; i < cnt; i++) {
-                const uint32_t len = pairs.len[i], dist = pairs.dist[i];
-                t.pairs_out[off + 1 + i] = pair_word(len, dist);
-                const uint32_t s1 = pos1 + len + 1;  // 1-based start of the continuation
-                uint32_t lim = s1 <= t.n ? t.n + 1 - s1 : 0;
-                if (lim > (uint32_t)w.fb) lim = (uint32_t)w.fb;
-                const uint8_t* a = t.buf + s1;
-                const uint32_t k = lim ? extend_run(a, a - dist - 1, 0, lim, t.n + 1 - s1) : 0;
-                t.pairs2_out[off + 1 + i] = pair2_word(len, k);
+                const uint32_t len = pairs.len[i];
+                t.pairs_out[off + 1 + i] = pair_word(len, pairs.dist[i]);
+                t.pairs2_out[off + 1 + i] = pair2_word(len, 0);
             }
         } else {
             atomicMax(w.overflow, 1u);
         }
     }
     t.idx[pos1] = where;
+    t.cnt[pos1] = (uint16_t)cnt;
+}
+
+// the continuation of one pair of the list of 1-based position pos1: GetMatchLen(len, dist, fb) one byte after the match
+__device__ __forceinline__ uint32_t pair_continuation(const uint8_t* buf1, uint32_t n, uint32_t fb, uint32_t pos1, uint32_t len, uint32_t dist) {
+    const uint32_t s1 = pos1 + len + 1;  // 1-based start of the continuation
+    if (s1 > n) return 0;
+    uint32_t lim = n + 1 - s1;
+    const uint32_t room = lim;
+    if (lim > fb) lim = fb;
+    const uint8_t* a = buf1 + s1;
+    return extend_run(a, a - dist - 1, 0, lim, room);
 }
 
 // One thread per hash-4 bucket.  A bucket with more than kLongChain positions hands the rest of its
@@ -329,15 +342,21 @@ __global__ void __launch_bounds__(256) lzb_mf_tree_kernel(MfWave w) {
     }
 }
 
-// Long buckets: one warp per chain, 32 consecutive insertions of the chain in flight.
+// Long buckets: one warp per chain, a rolling window of 32 consecutive insertions in flight.
 // The insertion of a position rewrites links strictly top-down: at any time it owns exactly two
 // "pending" slots (the reference's ptr0 / ptr1), every link above them is final, everything below
 // is untouched.  Pending slots hold kPending; a later insertion that needs such a link waits (it
 // retries in the next round), so it can never overtake an earlier one, and each insertion sees
 // exactly the tree the sequential order would have shown it.
+// A lane that finishes its insertion takes the next position of the chain at once (a drained batch
+// would leave the pipeline half empty: a frequent 4-gram in sorted-ish data degenerates the tree, every
+// insertion walks `cut` levels, and the chain's time is rounds per insertion x chain length).  The chain
+// itself is a linked list (`next`): one pointer-chasing load per round runs ahead of the insertions and
+// feeds a 32-entry FIFO held one entry per lane, and a round's loads -- the candidate's two links, the
+// window bytes, the chase -- are issued together, so a round costs one memory round trip.
 constexpr uint32_t kPending = 0xFFFFFFFFu;
 
-__global__ void __launch_bounds__(256) lzb_mf_long_kernel(MfWave w) {
+__global__ void __launch_bounds__(64) lzb_mf_long_kernel(MfWave w) {
     const int lane = threadIdx.x & 31;
     const uint32_t direct = w.bt4 ? 0 : 2;
     PairBuf pairs;
@@ -350,89 +369,248 @@ __global__ void __launch_bounds__(256) lzb_mf_long_kernel(MfWave w) {
         const uint32_t b = it.x;
         const TreeBlock t(w, b);
         volatile uint32_t* son = t.son;
-        uint32_t last = it.y, walk = it.z;
-        while (walk != 0) {
-            // the next (up to) 32 positions of the chain, one per lane
-            uint32_t pos1 = 0;
-            for (int k = 0; k < 32; k++) {
-                if (lane == k) pos1 = walk;
-                if (walk) walk = t.next[walk];
-            }
-            const bool active = pos1 != 0;
-            uint32_t root = __shfl_up_sync(kFull, pos1, 1);
-            if (lane == 0) root = last;
-            const unsigned am = __ballot_sync(kFull, active);
-            last = __shfl_sync(kFull, pos1, 31 - __clz(am));
-
-            uint32_t len_limit = 0, match_min_pos = 0, max_len = 1, cnt = 0, remaining = 0;
-            uint32_t ptr0 = 0, ptr1 = 0, len0 = direct, len1 = direct, cm = root;
-            int32_t count = w.cut;
-            bool done = !active;
-            if (active) {
-                remaining = t.n - (pos1 - 1);
-                len_limit = remaining < (uint32_t)w.fb ? remaining : (uint32_t)w.fb;
-                match_min_pos = pos1 > w.cyclic_size ? pos1 - w.cyclic_size : 0;
-                tree_prepairs(w, t, pos1, root, match_min_pos, pairs, cnt, max_len);
-                ptr0 = 2 * pos1 + 1;
-                ptr1 = 2 * pos1;
-                son[ptr0] = kPending;
-                son[ptr1] = kPending;
+        auto put = [&](uint32_t slot, uint32_t v) { son[slot] = v; };
+        // the chain ahead: FIFO entry i lives in lane (i & 31)
+        uint32_t q = lane == 0 ? it.z : 0u;
+        uint32_t qhead = 0, qcount = 1, tailpos = it.z, last_assigned = it.y;
+        bool chain_end = false;
+        // the insertion this lane is working on
+        bool done = true;
+        uint32_t pos1 = 0, len_limit = 0, match_min_pos = 0, max_len = 1, cnt = 0, remaining = 0;
+        uint32_t ptr0 = 0, ptr1 = 0, len0 = direct, len1 = direct, cm = 0, len = 0;
+        int32_t count = 0;
+        bool have_cmp = false;
+        for (;;) {
+            // the chase: one link ahead per round (every lane loads the same word)
+            const bool do_chase = !chain_end && qcount < 32;
+            uint32_t chased = 0;
+            if (do_chase) chased = t.next[tailpos];
+            // free lanes take the next positions of the chain, in order
+            const unsigned free_m = __ballot_sync(kFull, done);
+            uint32_t take = (uint32_t)__popc(free_m);
+            if (take > qcount) take = qcount;
+            if (take) {
+                const uint32_t r = (uint32_t)__popc(free_m & ((1u << lane) - 1u));  // rank among the free lanes
+                const uint32_t p = __shfl_sync(kFull, q, (qhead + r) & 31u);
+                const uint32_t before = __shfl_sync(kFull, q, (qhead + r + 31u) & 31u);
+                const uint32_t newest = __shfl_sync(kFull, q, (qhead + take - 1u) & 31u);
+                if (done && r < take) {
+                    pos1 = p;
+                    cm = r ? before : last_assigned;  // the bucket's previous position is where the descent starts
+                    remaining = t.n - (pos1 - 1);
+                    len_limit = remaining < (uint32_t)w.fb ? remaining : (uint32_t)w.fb;
+                    match_min_pos = pos1 > w.cyclic_size ? pos1 - w.cyclic_size : 0;
+                    tree_prepairs(w, t, pos1, cm, match_min_pos, pairs, cnt, max_len);
+                    ptr0 = 2 * pos1 + 1;
+                    ptr1 = 2 * pos1;
+                    son[ptr0] = kPending;
+                    son[ptr1] = kPending;
+                    len0 = len1 = direct;
+                    count = w.cut;
+                    have_cmp = false;
+                    done = false;
+                }
+                last_assigned = newest;
+                qhead += take;
+                qcount -= take;
             }
             __syncwarp();
-            const uint8_t* cur = t.buf + pos1;
-            // state of the compare with the current candidate (kept across retries)
-            bool have_cmp = false;
-            uint32_t len = 0;
-            while (__any_sync(kFull, !done)) {
-                if (!done) {
-                    if (cm <= match_min_pos || count == 0) {  // :231-235
-                        son[ptr0] = 0;
-                        son[ptr1] = 0;
-                        done = true;
-                    } else {
-                        const uint8_t* pby1 = t.buf + cm;
-                        if (!have_cmp) {
-                            len = len0 < len1 ? len0 : len1;
-                            if (pby1[len] == cur[len]) len = extend_run(cur, pby1, len + 1, len_limit, remaining);
-                            have_cmp = true;
+            if (!done) {
+                if (cm <= match_min_pos || count == 0) {  // BinTree.java:231-235
+                    put(ptr0, 0);
+                    put(ptr1, 0);
+                    done = true;
+                } else {
+                    const uint32_t kx = son[2 * cm], ky = son[2 * cm + 1];  // issued with the window bytes below
+                    const uint8_t* cur = t.buf + pos1;
+                    const uint8_t* pby1 = t.buf + cm;
+                    if (!have_cmp) {  // kept across retries
+                        len = len0 < len1 ? len0 : len1;
+                        if (pby1[len] == cur[len]) len = extend_run(cur, pby1, len + 1, len_limit, remaining);
+                        have_cmp = true;
+                    }
+                    const bool full = len == len_limit && max_len < len;  // :249-256 ends the insertion
+                    const bool right = !full && pby1[len] < cur[len];
+                    const bool ready = full ? (kx != kPending && ky != kPending) : (right ? ky != kPending : kx != kPending);
+                    if (ready) {
+                        count--;
+                        have_cmp = false;
+                        if (max_len < len) {
+                            max_len = len;
+                            pairs.put(cnt++, len, pos1 - cm - 1);
                         }
-                        const bool full = len == len_limit && max_len < len;  // :249-256 ends the insertion
-                        const bool right = !full && pby1[len] < cur[len];
-                        const uint32_t kx = son[2 * cm], ky = son[2 * cm + 1];
-                        const bool ready = full ? (kx != kPending && ky != kPending) : (right ? ky != kPending : kx != kPending);
-                        if (ready) {
-                            count--;
-                            have_cmp = false;
-                            if (max_len < len) {
-                                max_len = len;
-                                pairs.put(cnt++, len, pos1 - cm - 1);
-                            }
-                            if (full) {
-                                son[ptr1] = kx;
-                                son[ptr0] = ky;
-                                done = true;
-                            } else if (right) {
-                                son[ptr1] = cm;
-                                ptr1 = 2 * cm + 1;
-                                son[ptr1] = kPending;
-                                cm = ky;
-                                len1 = len;
-                            } else {
-                                son[ptr0] = cm;
-                                ptr0 = 2 * cm;
-                                son[ptr0] = kPending;
-                                cm = kx;
-                                len0 = len;
-                            }
+                        if (full) {
+                            put(ptr1, kx);
+                            put(ptr0, ky);
+                            done = true;
+                        } else if (right) {
+                            put(ptr1, cm);
+                            ptr1 = 2 * cm + 1;
+                            put(ptr1, kPending);
+                            cm = ky;
+                            len1 = len;
+                        } else {
+                            put(ptr0, cm);
+                            ptr0 = 2 * cm;
+                            put(ptr0, kPending);
+                            cm = kx;
+                            len0 = len;
                         }
                     }
                 }
-                __syncwarp();
+                if (done) tree_store_list(w, t, b, pos1, pairs, cnt);
             }
-            if (active) tree_store_list(w, t, b, pos1, pairs, cnt);
             __syncwarp();
+            if (do_chase) {
+                if (chased) {
+                    if (lane == (int)((qhead + qcount) & 31u)) q = chased;
+                    qcount++;
+                    tailpos = chased;
+                } else {
+                    chain_end = true;
+                }
+            }
+            if (chain_end && qcount == 0 && __all_sync(kFull, done)) break;
         }
     }
+}
+
+// ---- list compaction: temporary lists -> position-ordered lists in the wave's pool -----------------
+// The tree threads allocate their lists in the order they finish, so the lists of neighbouring
+// positions are scattered over the block's temporary area.  The parser walks positions in order;
+// compacting the lists in position order turns its three reads per position (idx, pairs, pair2) into
+// forward walks (measured on the parser: DRAM traffic per input byte, profiles/r02_*), sizes the
+// resident lists exactly (6 bytes per pair word instead of a worst-case 36 bytes per input byte), and
+// frees the match finder's scratch for the next group of blocks.
+__device__ __forceinline__ uint32_t cta_exclusive_scan_256(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(kFull, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < 8 ? s_warp[lane] : 0, z = w;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(kFull, z, d);
+            if (lane >= d) z += y;
+        }
+        if (lane < 8) s_warp[lane] = z - w;
+        if (lane == 7) s_warp[8] = z;
+    }
+    __syncthreads();
+    const uint32_t r = s_warp[warp] + x - v;
+    if (total) *total = s_warp[8];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(256) lzb_list_tile_sums(MfWave w, uint32_t tiles_max, uint32_t* tile_sum) {
+    __shared__ uint32_t s_warp[9];
+    const uint32_t b = blockIdx.y, t = blockIdx.x;
+    if (w.in_len[b] > (uint64_t)w.np - 1) return;  // flagged by the link kernel
+    const uint32_t n = (uint32_t)w.in_len[b];
+    if ((uint64_t)t * kListTile >= n) return;
+    const uint16_t* cnt = w.cnt + (size_t)b * w.np;
+    const uint32_t p0 = t * kListTile + threadIdx.x * 8;
+    uint32_t s = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) {
+        const uint32_t p = p0 + k;
+        const uint32_t c = p < n ? cnt[p + 1] : 0;
+        s += c ? c + 1 : 0;
+    }
+    uint32_t total;
+    cta_exclusive_scan_256(s, s_warp, &total);
+    if (threadIdx.x == 0) tile_sum[(size_t)b * tiles_max + t] = total;
+}
+
+__global__ void __launch_bounds__(256) lzb_list_scan_tiles(MfWave w, uint32_t tiles_max, uint32_t* tile_sum, uint32_t* w_total) {
+    __shared__ uint32_t s_warp[9];
+    const uint32_t b = blockIdx.x;
+    const uint32_t n = w.in_len[b] > (uint64_t)w.np - 1 ? 0u : (uint32_t)w.in_len[b];
+    const uint32_t tiles = (n + kListTile - 1) / kListTile;
+    uint32_t* ts = tile_sum + (size_t)b * tiles_max;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < tiles; base += 256) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < tiles ? ts[i] : 0;
+        uint32_t total;
+        const uint32_t ex = cta_exclusive_scan_256(v, s_warp, &total);
+        if (i < tiles) ts[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) w_total[b] = carry;
+}
+
+__global__ void __launch_bounds__(256) lzb_list_gather(MfWave w, uint32_t tiles_max, const uint32_t* tile_off, const BlockLists* lists,
+                                                       uint8_t* pool) {
+    __shared__ uint32_t s_warp[9];
+    const uint32_t b = blockIdx.y, t = blockIdx.x;
+    const uint32_t n = (uint32_t)w.in_len[b];
+    if ((uint64_t)t * kListTile >= n) return;
+    const uint16_t* cnt = w.cnt + (size_t)b * w.np;
+    const uint32_t* idx_tmp = w.idx + (size_t)b * w.np;
+    const uint32_t* pairs_tmp = w.pairs + (size_t)b * w.pair_cap;
+    const uint16_t* pairs2_tmp = w.pairs2 + (size_t)b * w.pair_cap;
+    const BlockLists L = lists[b];
+    const uint8_t* buf1 = w.in + w.in_off[b] - 1;  // buf1[pos1] is the byte at 1-based position pos1
+    uint32_t* idx = reinterpret_cast<uint32_t*>(pool + L.idx_off);
+    uint32_t* pairs = reinterpret_cast<uint32_t*>(pool + L.pairs_off);
+    uint16_t* pairs2 = reinterpret_cast<uint16_t*>(pool + L.pairs2_off);
+    const uint32_t p0 = t * kListTile + threadIdx.x * 8;
+    uint32_t c[8], s = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) {
+        const uint32_t p = p0 + k;
+        c[k] = p < n ? cnt[p + 1] : 0;
+        s += c[k] ? c[k] + 1 : 0;
+    }
+    uint32_t off = tile_off[(size_t)b * tiles_max + t] + cta_exclusive_scan_256(s, s_warp, nullptr);
+#pragma unroll 1
+    for (uint32_t k = 0; k < 8; k++) {
+        const uint32_t p = p0 + k;
+        if (p >= n) break;
+        if (c[k] == 0) {
+            idx[p + 1] = kMfEmpty;
+            continue;
+        }
+        idx[p + 1] = off;
+        const uint32_t from = idx_tmp[p + 1];
+        pairs[off] = c[k];
+        pairs2[off] = 0;
+        for (uint32_t i = 1; i <= c[k]; i++) {
+            const uint32_t wd = pairs_tmp[from + i], w2 = pairs2_tmp[from + i];
+            const uint32_t len = pair_len(wd, w2);
+            pairs[off + i] = wd;
+            pairs2[off + i] = pair2_word(len, pair_continuation(buf1, n, (uint32_t)w.fb, p + 1, len, pair_dist(wd)));
+        }
+        off += c[k] + 1;
+    }
+}
+
+cudaError_t launch_list_scan(const MfWave& w, uint32_t max_len, uint32_t* tile_sum, uint32_t* w_total, cudaStream_t st) {
+    if (w.n_blocks == 0) return cudaSuccess;
+    const uint32_t tiles_max = (max_len + kListTile - 1) / kListTile;
+    if (tiles_max) {
+        lzb_list_tile_sums<<<dim3(tiles_max, w.n_blocks), 256, 0, st>>>(w, tiles_max, tile_sum);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    lzb_list_scan_tiles<<<w.n_blocks, 256, 0, st>>>(w, tiles_max ? tiles_max : 1, tile_sum, w_total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_list_gather(const MfWave& w, uint32_t max_len, const uint32_t* tile_off, const BlockLists* lists, uint8_t* pool,
+                               cudaStream_t st) {
+    const uint32_t tiles_max = (max_len + kListTile - 1) / kListTile;
+    if (w.n_blocks == 0 || tiles_max == 0) return cudaSuccess;
+    lzb_list_gather<<<dim3(tiles_max, w.n_blocks), 256, 0, st>>>(w, tiles_max, tile_off, lists, pool);
+    return cudaGetLastError();
 }
 
 // `ev` (optional, LZB_ENC_TIMING): three events recorded after the link, tree and long kernels
@@ -449,7 +627,9 @@ cudaError_t launch_mf(const MfWave& w, uint32_t max_len, int num_sms, cudaStream
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[1], st);
-    lzb_mf_long_kernel<<<num_sms * 8, 256, 0, st>>>(w);
+    // small CTAs: a warp that runs out of chains gives its slot back at once (the last long chains keep a
+    // few warps busy for a long time, and the next group's kernels are waiting on the other stream)
+    lzb_mf_long_kernel<<<num_sms * 32, 64, 0, st>>>(w);
     if (ev) cudaEventRecord(ev[2], st);
     return cudaGetLastError();
 }

@@ -1396,9 +1396,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) lzb_parse_kernel(ParseArgs a) {
         uint32_t b = 0;
         if (lane == 0) b = atomicAdd(a.ticket, 1u);
         b = __shfl_sync(kFull, b, 0);
-        if (b >= a.mf.n_blocks) break;
+        if (b >= a.n_blocks) break;
         if (a.order) b = a.order[b];
-        const uint32_t n = (uint32_t)a.mf.in_len[b];
+        const uint32_t n = (uint32_t)a.in_len[b];
         uint8_t* out = a.out + a.out_off[b];
         uint64_t cap = a.out_cap[b];
         uint64_t header = 0;
@@ -1450,11 +1450,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1) lzb_parse_kernel(ParseArgs a) {
         e.gopt = reinterpret_cast<OptNode*>(a.opt_scratch) + slot * (size_t)kNumOpts;
         e.ctx = ctx;
         e.L = L;
-        e.data = a.mf.in + a.mf.in_off[b];
+        e.data = a.in + a.in_off[b];
         e.n = n;
-        e.idx = a.mf.idx + (size_t)b * a.mf.np;
-        e.pairs = a.mf.pairs + (size_t)b * a.mf.pair_cap;
-        e.pairs2 = a.mf.pairs2 + (size_t)b * a.mf.pair_cap;
+        const BlockLists bl = a.lists[b];
+        e.idx = reinterpret_cast<const uint32_t*>(a.pool + bl.idx_off);
+        e.pairs = reinterpret_cast<const uint32_t*>(a.pool + bl.pairs_off);
+        e.pairs2 = reinterpret_cast<const uint16_t*>(a.pool + bl.pairs2_off);
         e.lane = lane;
         e.lc = a.lc;
         e.lp = a.lp;

@@ -79,14 +79,27 @@ struct EncodeArgs {
     int32_t tune_warps = 0;      // LZB_ENC_WARPS: parser streams per SM (0 = automatic)
     int32_t tune_pair_mul = 0;   // LZB_PAIR_MUL: initial match-pair budget in slots per input byte (0 = default)
     int32_t tune_lit = -1;       // LZB_ENC_LIT: 0 = literal coders in shared memory, 1 = in global memory (-1 = automatic)
+    int32_t tune_group = 0;      // LZB_ENC_GROUP: at most this many blocks per match-finder group (0 = what the scratch budget allows)
+    int64_t tune_pool = 0;       // LZB_ENC_POOL_MB: cap of the list pool in bytes (0 = sized from the batch): small values force many waves
     bool tune_fifo = false;      // LZB_ENC_FIFO: plain block order inside a wave
     bool tune_timing = false;    // LZB_ENC_TIMING: phase times of every wave on stderr
 };
 
-// device scratch owned by an encoder handle (grow-only)
+// device scratch owned by an encoder handle (grow-only): the match finder's group scratch (`p`), the wave's
+// list pool and the parser's per-slot areas
+constexpr int kEncGroupsInFlight = 6;
 struct EncScratch {
-    void* p = nullptr;
-    size_t cap = 0;
+    void* gp[kEncGroupsInFlight] = {};        // group scratch, one per group in flight
+    size_t gcap[kEncGroupsInFlight] = {};
+    cudaStream_t gs[kEncGroupsInFlight] = {};  // [0] unused (the caller's stream)
+    cudaEvent_t gev[kEncGroupsInFlight] = {};
+    bool streams_ready = false;
+    uint32_t* h_totals = nullptr;  // pinned: per-group pair totals + overflow flag, one row per group in flight
+    size_t h_totals_cap = 0;
+    void* pool = nullptr;
+    size_t pool_cap = 0;
+    void* fixed = nullptr;
+    size_t fixed_cap = 0;
     void release();
 };
 
@@ -96,7 +109,7 @@ constexpr int kEncMaxWarps = 14;           // ... with the literal coders in glo
 
 // where the match finder left the lists of the first block of a batch (trace tap)
 struct MfTrace {
-    const uint32_t* idx = nullptr;    // [len + 1], 1-based: offset into pairs or 0xFFFFFFFF
+    const uint32_t* idx = nullptr;    // [len + 1], 1-based: offset into pairs or 0xFFFFFFFF (the match finder's temporary lists)
     const uint32_t* pairs = nullptr;  // count, then count x pair_word (lzb_encode.cuh)
     const uint16_t* pairs2 = nullptr; // pair2_word per pair
     uint32_t pair_words = 0;          // words in use

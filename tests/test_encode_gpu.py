@@ -329,3 +329,15 @@ def test_encode_8mib_blocks_c4_all_classes(lzb, oracle, corpus):
     p.update(dict_size=1 << 23, fb=273)
     n, size = 4, 1 << 23
     _batch_equals_oracle(lzb, oracle, p, corpus.generate(size, n, corpus.MIXED, 4), n, size, threads=4)
+
+
+def test_encode_groups_and_waves(lzb, oracle, corpus, monkeypatch):
+    """The match finder works through a batch in groups (its scratch is reused) and the parser in waves (as many
+    groups as fit the list pool).  Tiny limits force 9 groups and several waves on a small batch; every block ==
+    oracle whatever the cut (lzb_encode.cu, run_encode)."""
+    monkeypatch.setenv("LZB_ENC_GROUP", "5")
+    monkeypatch.setenv("LZB_ENC_POOL_MB", "3")
+    blocks = [corpus.generate(60000 + 7001 * (i % 9), 1, i % 4, 45, i).tobytes() for i in range(43)] + [b"", b"q"]
+    got = _gpu_streams(lzb, BASE, blocks)
+    for i, b in enumerate(blocks):
+        assert got[i] == oracle.encode(b, oracle.props(**BASE), alone=True), i
