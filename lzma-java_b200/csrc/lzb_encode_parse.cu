@@ -223,7 +223,7 @@ __host__ __device__ inline SliceLayout make_slice(int lc, int lp, int pb, int fb
     const ModelLayout L = make_layout(lc, lp, pb);
     const uint32_t table = (uint32_t)(fb - 1);
     // a DP step touches nodes [cur - 2fb - 1, cur + 2fb + 1]
-    const uint32_t ring_nodes = ((uint32_t)(4 * fb + 3) + 31) & ~31u;
+    const uint32_t ring_nodes = ((uint32_t)(4 * fb + 3) + 7) & ~7u;
     SliceLayout s;
     uint32_t o = (uint32_t)(L.n_fixed + (with_lit ? L.n_literal : 0)) * 2;
     o = (o + 15) & ~15u;
@@ -233,9 +233,11 @@ __host__ __device__ inline SliceLayout make_slice(int lc, int lp, int pb, int fb
     s.slot_prices = o;  o += 256 * 2;
     s.align_prices = o; o += 16 * 2;
     s.len_prices = o;   o += ((2u << pb) * table * 2 + 15) & ~15u;
-    s.len_counters = o; o += 32 * 4;
-    s.md = o;           o += 288 * 4;
-    s.md2 = o;          o += 288 * 4;
+    s.len_counters = o; o += 32 * 4;  // [2][16]
+    // a position has at most fb - 1 pairs (lengths 2 .. fb, strictly increasing) and the parser may append one
+    const uint32_t md_entries = ((uint32_t)fb + 1 + 31) & ~31u;
+    s.md = o;           o += md_entries * 4;
+    s.md2 = o;          o += md_entries * 4;
     o = (o + 15) & ~15u;
     s.ring = o;         o += ring_nodes * 32;
     s.total = o;
@@ -1391,12 +1393,15 @@ __global__ void __launch_bounds__(MAXW * 32, 1) lzb_parse_kernel(ParseArgs a) {
     }
     __syncwarp();
 
+    // The first block of a warp is fixed by its place (the warps of a CTA take consecutive entries of the
+    // cost-sorted order: an SM's streams then belong to the same kind of data and run the same parts of this
+    // kernel, which is what its instruction cache can hold); later blocks are drawn from the ticket counter.
+    const uint32_t slots = gridDim.x * (uint32_t)warps;
+    uint32_t b = (uint32_t)slot;
     #pragma unroll 1
-    for (;;) {
-        uint32_t b = 0;
-        if (lane == 0) b = atomicAdd(a.ticket, 1u);
-        b = __shfl_sync(kFull, b, 0);
+    for (;; ) {
         if (b >= a.n_blocks) break;
+        const uint32_t ticket_b = b;
         if (a.order) b = a.order[b];
         const uint32_t n = (uint32_t)a.in_len[b];
         uint8_t* out = a.out + a.out_off[b];
@@ -1469,6 +1474,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) lzb_parse_kernel(ParseArgs a) {
         e.run();
         if (lane == 0) a.out_len[b] = (uint64_t)ctx->rc.pos > cap ? ~0ull : (uint64_t)ctx->rc.pos + header;
         __syncwarp();
+        (void)ticket_b;
+        b = 0;
+        if (lane == 0) b = slots + atomicAdd(a.ticket, 1u);
+        b = __shfl_sync(kFull, b, 0);
     }
 }
 

@@ -105,7 +105,7 @@ struct EncScratch {
 
 constexpr uint64_t kEncMaxBlockBytes = (1ull << 30) - 1;  // one stream; BinTree.Normalize (BinTree.java:358-375) is not built
 constexpr int kEncWarpsLitSmem = 9;        // parser streams per SM, literal coders in shared memory (shared memory decides, see parse_geometry)
-constexpr int kEncMaxWarps = 14;           // ... with the literal coders in global memory: 64 K registers / (14 x 32) = 146 per thread
+constexpr int kEncMaxWarps = 14;           // ... with the literal coders in global memory (15 and 16 measured no faster: profiles/r02_parse_residency_ab.log)
 
 // where the match finder left the lists of the first block of a batch (trace tap)
 struct MfTrace {
