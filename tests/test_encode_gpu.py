@@ -341,3 +341,49 @@ def test_encode_groups_and_waves(lzb, oracle, corpus, monkeypatch):
     got = _gpu_streams(lzb, BASE, blocks)
     for i, b in enumerate(blocks):
         assert got[i] == oracle.encode(b, oracle.props(**BASE), alone=True), i
+
+
+def test_encode_device_outputs_stay_inside_their_capacity(lzb, oracle, corpus):
+    """lzb_enc_code_batch_device writes block i only inside d_out[out_off[i] .. out_off[i] + out_cap[i]): canaries between the
+    regions survive, a block whose capacity is too small reports UINT64_MAX and leaves its neighbours alone, and a block longer
+    than the declared max_in_len is refused (LZB_E_ARG) instead of overrunning the match finder's scratch."""
+    import torch
+    dev = torch.device("cuda:0")
+    n, size, gap = 24, 30000, 512
+    data = corpus.generate(size, n, corpus.MIXED, 46)
+    cap = lzb.enc_bound(size) + 13
+    caps = np.full(n, cap, dtype=np.int64)
+    caps[5] = 100          # far too small
+    pitch = cap + gap
+    d_in = torch.from_numpy(data).to(dev)
+    off = torch.arange(n, dtype=torch.int64, device=dev) * size
+    ln = torch.full((n,), size, dtype=torch.int64, device=dev)
+    ooff = torch.arange(n, dtype=torch.int64, device=dev) * pitch + gap
+    ocap = torch.from_numpy(caps).to(dev)
+    d_out = torch.full((n * pitch + gap,), 0xA5, dtype=torch.uint8, device=dev)
+    d_len = torch.zeros(n, dtype=torch.int64, device=dev)
+    enc = _encoder(lzb, BASE)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        enc.code_batch_device(d_in.data_ptr(), off.data_ptr(), ln.data_ptr(), n, size, d_out.data_ptr(), ooff.data_ptr(),
+                              ocap.data_ptr(), d_len.data_ptr(), True, st.cuda_stream)
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy()
+    lens = d_len.cpu().numpy()
+    keep = np.ones(out.size, dtype=bool)
+    for i in range(n):
+        a = gap + i * pitch
+        keep[a: a + int(caps[i])] = False
+        if i == 5:
+            assert lens[i] == -1  # UINT64_MAX
+            continue
+        ref = oracle.encode(data[i * size:(i + 1) * size], oracle.props(**BASE), alone=True)
+        assert out[a: a + int(lens[i])].tobytes() == ref, i
+    assert (out[keep] == 0xA5).all()
+    # a block longer than max_in_len
+    with pytest.raises(lzb.LzbError) as ei:
+        with torch.cuda.stream(st):
+            enc.code_batch_device(d_in.data_ptr(), off.data_ptr(), ln.data_ptr(), n, size - 1, d_out.data_ptr(), ooff.data_ptr(),
+                                  ocap.data_ptr(), d_len.data_ptr(), True, st.cuda_stream)
+    assert ei.value.code == lzb.LZB_E_ARG
+    enc.close()
