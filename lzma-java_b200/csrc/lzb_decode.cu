@@ -443,6 +443,7 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
     int status = 1;
     uint32_t pos = 0;
     uint32_t marks_done = 0;  // progress marks already reported for this stream
+    uint32_t next_mark = PROGRESS && a.marks > 1 ? a.mark_step : 0xFFFFFFFFu;  // output position of the next mark to report
     if (in_len < LZB_KERNEL_HEADER) {
         status = 0;  // "input .lzma file is too short" / "Can't read stream size"
     } else if (in_len - LZB_KERNEL_HEADER >= 0xFFFFFFF0ull || cap64 >= 0xFFFFFFF0ull) {
@@ -574,6 +575,9 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
                         break;
                     }
                     evlen = (uint32_t)ev | (len << 2);
+                    // the "a progress mark was passed" bit rides in the event word: the other lanes then need not wait
+                    // for the shuffled position to find out (a shared-memory-latency stall per match otherwise)
+                    if (PROGRESS && ev == EV_MATCH && len != 0 && pos >= next_mark) evlen |= 0x80000000u;
                 }
                 evlen = __shfl_sync(kFull, evlen, 0);
                 // the tail of the previous match is still in registers: store it now that its loads
@@ -590,15 +594,16 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
                     break;
                 }
                 // OutWindow.CopyBlock (OutWindow.java:53-67), all lanes: out[pos+k] = out[pos-d+(k mod d)].
-                const uint32_t len = evlen >> 2;
+                const uint32_t len = (evlen >> 2) & 0x1FFu;
                 const uint32_t d = __shfl_sync(kFull, rep0, 0) + 1;
                 pos = __shfl_sync(kFull, pos, 0);
-                if (PROGRESS && marks_done + 1 < a.marks && pos >= (marks_done + 1) * a.mark_step) {
+                if (PROGRESS && (evlen >> 31)) {
                     // everything below `pos` is stored (the pending tail went out above)
                     uint32_t reached = pos / a.mark_step;
                     if (reached > a.marks - 1) reached = a.marks - 1;
                     report_progress(a, marks_done, reached, lane);
                     marks_done = reached;
+                    next_mark = marks_done + 1 < a.marks ? (marks_done + 1) * a.mark_step : 0xFFFFFFFFu;
                 }
                 __syncwarp();  // order earlier stores (lane 0's literals, other lanes' copies) before these loads
                 const uint8_t* src = out + pos - d;

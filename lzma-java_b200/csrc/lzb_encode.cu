@@ -216,6 +216,25 @@ cudaError_t parse_wave(const EncodeArgs& a, const Plan& P, const Fixed& F, const
         order.resize(wb);
         for (uint32_t i = 0; i < wb; i++) order[i] = i;
         std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return wv.cost[x] > wv.cost[y]; });
+        if (!a.tune_blocked) {
+            // Warp w of CTA c starts on order[c * warps + w].  At 12-14 streams per SM the parser is bound by the SM's
+            // instruction issue, so what counts is that every SM gets the same amount of work: the blocks that start at
+            // once are dealt to the CTAs like cards, heaviest first, back and forth (CTA 0..G-1, G-1..0, ...), each CTA
+            // taking as many as it has warps below n_blocks.  Blocks drawn later by ticket keep the decreasing order.
+            const uint32_t first = std::min<uint32_t>(wb, (uint32_t)grid * (uint32_t)warps);
+            std::vector<uint32_t> dealt(first), fill((size_t)grid, 0);
+            uint32_t k = 0;
+            for (uint32_t pass = 0; k < first; pass++) {
+                for (int i = 0; i < grid && k < first; i++) {
+                    const uint32_t c = (pass & 1) ? (uint32_t)(grid - 1 - i) : (uint32_t)i;
+                    const uint32_t p = c * (uint32_t)warps + fill[c];
+                    if (fill[c] >= (uint32_t)warps || p >= first) continue;
+                    dealt[p] = order[k++];
+                    fill[c]++;
+                }
+            }
+            std::copy(dealt.begin(), dealt.end(), order.begin());
+        }
         e = cudaMemcpyAsync(F.order, order.data(), (size_t)wb * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) return e;
         pa.order = F.order;

@@ -82,6 +82,7 @@ struct EncodeArgs {
     int32_t tune_group = 0;      // LZB_ENC_GROUP: at most this many blocks per match-finder group (0 = what the scratch budget allows)
     int64_t tune_pool = 0;       // LZB_ENC_POOL_MB: cap of the list pool in bytes (0 = sized from the batch): small values force many waves
     bool tune_fifo = false;      // LZB_ENC_FIFO: plain block order inside a wave
+    bool tune_blocked = false;   // LZB_ENC_BLOCKED: cost-sorted order, neighbours on one SM (no dealing across the SMs)
     bool tune_timing = false;    // LZB_ENC_TIMING: phase times of every wave on stderr
 };
 
