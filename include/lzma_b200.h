@@ -113,9 +113,15 @@ int lzb_enc_code_batch(lzb_enc *e, const uint8_t *in, const uint64_t *in_off,
 
 /* Same batch with every pointer in DEVICE memory of the handle's device;
  * work is enqueued on `cuda_stream` (a cudaStream_t passed as void*, NULL =
- * the handle's own stream) and the call returns after enqueueing.
- * out_len[i] is valid once the stream has been synchronised; a block whose
- * capacity was too small reports out_len[i] = UINT64_MAX. */
+ * the handle's own stream).  The call is BLOCKING: between the match finder
+ * and the parser the host reads back the per-block list sizes (to place the
+ * lists and to order the blocks), so it synchronises `cuda_stream` several
+ * times and returns when the batch is done; out_len[i] is valid on return.
+ * It may allocate device memory (grow-only scratch of the handle) and cannot
+ * be captured into a CUDA graph.  A handle serves one call at a time.  A
+ * block whose capacity was too small reports out_len[i] = UINT64_MAX.
+ * max_in_len >= every in_len[i] sizes the scratch; a longer block makes the
+ * call fail with LZB_E_ARG instead of touching memory it was not given. */
 int lzb_enc_code_batch_device(lzb_enc *e, const uint8_t *d_in,
                               const uint64_t *d_in_off, const uint64_t *d_in_len,
                               uint32_t n, uint64_t max_in_len,
@@ -167,7 +173,12 @@ int lzb_dec_code_batch(lzb_dec *d, const uint8_t *in, const uint64_t *in_off,
                        int32_t *status);
 
 /* Same batch with every pointer in DEVICE memory; enqueued on `cuda_stream`
- * (NULL = the handle's own stream), asynchronous. */
+ * (NULL = the handle's own stream).  The call synchronises the stream once
+ * (it scans the n stream headers on the device to pick the kernel variant and
+ * size the model scratch) and returns after the decode kernel has been
+ * enqueued: d_out, d_out_len and d_status are valid once `cuda_stream` has
+ * been synchronised.  A handle serves one call at a time (the calls share
+ * its ticket counter and scratch); not capturable into a CUDA graph. */
 int lzb_dec_code_batch_device(lzb_dec *d, const uint8_t *d_in,
                               const uint64_t *d_in_off, const uint64_t *d_in_len,
                               uint32_t n, uint8_t *d_out,

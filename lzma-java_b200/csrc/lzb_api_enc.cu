@@ -26,7 +26,7 @@ struct lzb_enc {
     DevBuf d_in, d_out, d_meta;
     PinBuf h_meta;
     // developer / test hooks (DESIGN.md "test hooks"), read ONCE when the handle is created
-    int32_t tune_warps = 0, tune_pair_mul = 0, tune_lit = -1, tune_group = 0;
+    int32_t tune_warps = 0, tune_pair_mul = 0, tune_lit = -1, tune_group = 0, tune_inflight = 0;
     int64_t tune_pool = 0;
     bool tune_fifo = false, tune_timing = false, tune_blocked = false;
 };
@@ -51,6 +51,7 @@ lzb_enc* lzb_enc_create(int device) {
     if (const char* v = getenv("LZB_ENC_POOL_MB")) e->tune_pool = atoll(v) > 0 ? atoll(v) << 20 : 0;
     e->tune_fifo = getenv("LZB_ENC_FIFO") != nullptr;
     e->tune_blocked = getenv("LZB_ENC_BLOCKED") != nullptr;
+    if (const char* v = getenv("LZB_ENC_INFLIGHT")) e->tune_inflight = atoi(v) > 0 ? atoi(v) : 0;
     e->tune_timing = getenv("LZB_ENC_TIMING") != nullptr;
     return e;
 }
@@ -148,6 +149,7 @@ int lzb_enc_code_batch_device(lzb_enc* e, const uint8_t* d_in, const uint64_t* d
     a.tune_pool = e->tune_pool;
     a.tune_fifo = e->tune_fifo;
     a.tune_blocked = e->tune_blocked;
+    a.tune_inflight = e->tune_inflight;
     a.tune_timing = e->tune_timing;
     int launches = 0;
     cudaError_t err = lzb::run_encode(a, e->scratch, e->num_sms, st, &launches);

@@ -326,16 +326,17 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
     if (e != cudaSuccess) return e;
     carve_fixed((uint8_t*)scratch.fixed, a.n, slots, slots * P.lit_per_slot, &F);
 
-    // ---- groups: K of them are in flight, each with its own scratch and stream; together they may take 40 % of
+    // ---- groups: K of them are in flight, each with its own scratch and stream; together they may take 45 % of
     // the budget.  Many small groups beat few large ones: lzb_mf_long_kernel ends on its longest hash bucket (a
     // serial chain: ~0.25 s per MiB of ordered records, whatever the group's size), and while a few warps finish
     // those chains the other groups' kernels fill the GPU.
-    const int K = mf_only ? 1 : kEncGroupsInFlight;
+    int K = mf_only ? 1 : kEncGroupsDefault;
+    if (!mf_only && a.tune_inflight > 0) K = std::min<int>(a.tune_inflight, kEncGroupsInFlight);
     auto group_bytes = [&](uint32_t gb, uint32_t pm) {
         return carve_group(nullptr, gb, P.np, P.hash_stride, pair_cap_for(pm, a.max_in_len), nullptr, nullptr, nullptr);
     };
     uint32_t gmax = std::min<uint32_t>(a.n, 32768);
-    const size_t group_budget = std::max<size_t>((budget - std::min(budget, fixed_bytes)) / 5 * 2 / (size_t)K, group_bytes(1, pair_mul));
+    const size_t group_budget = std::max<size_t>((budget - std::min(budget, fixed_bytes)) / 20 * 9 / (size_t)K, group_bytes(1, pair_mul));
     if (group_bytes(gmax, pair_mul) > group_budget) {
         uint32_t lo = 1, hi = gmax;  // group_bytes is monotonic: binary search the largest count that fits
         while (lo < hi) {
@@ -345,7 +346,12 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
         }
         gmax = lo;
     }
-    if (!mf_only && gmax * (uint32_t)K > a.n) gmax = std::max<uint32_t>((a.n + (uint32_t)K - 1) / (uint32_t)K, 1);  // at least K groups when the batch allows
+    if (!mf_only) {
+        // Whole rounds of K equal groups: the last groups of a ragged batch would otherwise run alone, on a GPU that the
+        // match finder's serial chains cannot fill (2048 blocks as 13 x 154 + 46: the last two groups took 0.5 s by themselves).
+        const uint32_t rounds = (a.n + gmax * (uint32_t)K - 1) / (gmax * (uint32_t)K);
+        gmax = std::max<uint32_t>((a.n + rounds * (uint32_t)K - 1) / (rounds * (uint32_t)K), 1);
+    }
     if (a.tune_group > 0) gmax = std::min<uint32_t>(gmax, (uint32_t)a.tune_group);  // test knob: small groups
 
     // ---- list pool: what the batch is expected to need (4 B per input byte + 6 B per pair word at 4.5 pair words

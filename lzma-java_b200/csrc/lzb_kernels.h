@@ -82,13 +82,15 @@ struct EncodeArgs {
     int32_t tune_group = 0;      // LZB_ENC_GROUP: at most this many blocks per match-finder group (0 = what the scratch budget allows)
     int64_t tune_pool = 0;       // LZB_ENC_POOL_MB: cap of the list pool in bytes (0 = sized from the batch): small values force many waves
     bool tune_fifo = false;      // LZB_ENC_FIFO: plain block order inside a wave
+    int32_t tune_inflight = 0;   // LZB_ENC_INFLIGHT: match-finder groups in flight (0 = kEncGroupsDefault)
     bool tune_blocked = false;   // LZB_ENC_BLOCKED: cost-sorted order, neighbours on one SM (no dealing across the SMs)
     bool tune_timing = false;    // LZB_ENC_TIMING: phase times of every wave on stderr
 };
 
 // device scratch owned by an encoder handle (grow-only): the match finder's group scratch (`p`), the wave's
 // list pool and the parser's per-slot areas
-constexpr int kEncGroupsInFlight = 6;
+constexpr int kEncGroupsInFlight = 8;   // buffers / streams a handle can hold; kEncGroupsDefault of them are used unless tuned
+constexpr int kEncGroupsDefault = 6;
 struct EncScratch {
     void* gp[kEncGroupsInFlight] = {};        // group scratch, one per group in flight
     size_t gcap[kEncGroupsInFlight] = {};
