@@ -110,7 +110,8 @@ int pick_dec_mode(uint32_t max_lclp1, uint32_t max_pb1, uint64_t resident, int n
 int dec_enqueue(lzb_dec* d, const uint8_t* d_in, const uint64_t* d_in_off, const uint64_t* d_in_len, uint32_t n,
                 uint8_t* d_out, const uint64_t* d_out_off, const uint64_t* d_out_cap, uint64_t* d_out_len,
                 int32_t* d_status, uint32_t max_lclp1, uint32_t max_pb1, int mode, uint32_t* ticket, cudaStream_t st, uint32_t region = 0,
-                uint32_t n_regions = 1, uint32_t* progress = nullptr, uint32_t marks = 0, uint32_t mark_step = 0) {
+                uint32_t n_regions = 1, uint32_t* progress = nullptr, uint32_t* progress_dev = nullptr, uint32_t marks = 0,
+                const uint32_t* mark_at = nullptr) {
     lzb::DecodeArgs a;
     a.in = d_in;
     a.in_off = d_in_off;
@@ -125,8 +126,9 @@ int dec_enqueue(lzb_dec* d, const uint8_t* d_in, const uint64_t* d_in_off, const
     a.lit_scratch = nullptr;
     a.lit_stride = 0;
     a.progress = progress;
+    a.progress_dev = progress_dev;
     a.marks = marks;
-    a.mark_step = mark_step;
+    for (uint32_t m = 0; m < marks && m < lzb::kDecMaxMarks; m++) a.mark_at[m] = mark_at[m];
     if (mode != lzb::kDecSmem && max_lclp1) {
         a.lit_stride = (size_t)(mode == lzb::kDecHybrid ? 0x200 : 0x300) << (max_lclp1 - 1);
         const size_t slots = (size_t)d->num_sms * lzb::dec_mode_warps(mode);
@@ -331,13 +333,18 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
     // streams whose output below that mark is complete (DecodeArgs::progress, in pinned host
     // memory), and this thread issues one strided copy per (chunk, mark) as the counts fill up.
     // Other layouts are copied chunk by chunk after their kernel.
-    constexpr uint32_t kMaxMarks = 32;
-    uint32_t kMarks = 8;
-    if (d->env_marks >= 1 && d->env_marks <= (int)kMaxMarks) kMarks = (uint32_t)d->env_marks;  // test hook
+    // Every copy but the last one hides behind the decoders, so the marks are not evenly spaced: 1/4, 1/2, 3/4,
+    // 7/8, 15/16, 31/32 of a row and its end -- few wide copies first (a strided copy of thousands of rows has a
+    // cost of its own, and so has a mark inside the kernel), and only 1/32 of the output left to fetch once the
+    // kernel has ended.  LZB_DEC_MARKS = k asks for k even marks instead (test hook).
+    constexpr uint32_t kMaxMarks = lzb::kDecMaxMarks;
+    const uint32_t kMarks = kMaxMarks;  // stride of the progress counters per chunk
+    const uint32_t even_marks = d->env_marks >= 1 && d->env_marks <= (int)kMaxMarks ? (uint32_t)d->env_marks : 0;
     struct Rows {
         bool on = false;
         uint64_t pitch = 0, cap = 0;
-        uint32_t step = 0, marks = 0, issued = 0;
+        uint32_t marks = 0, issued = 0;
+        uint32_t at[lzb::kDecMaxMarks] = {};  // at[m] = end column of mark m (a multiple of 512 but for the last = cap)
     };
     std::vector<Rows> rows(n_chunks);
     std::vector<char> span_copy(n_chunks, 1);
@@ -352,8 +359,17 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
         for (uint32_t i = 1; i < cnt && r.on; i++)
             r.on = out_cap[s0 + i] == r.cap && out_off[s0 + i] == out_off[s0] + (uint64_t)i * r.pitch;
         if (!r.on) continue;
-        r.step = (uint32_t)(((r.cap + kMarks - 1) / kMarks + 511) & ~(uint64_t)511);
-        r.marks = (uint32_t)((r.cap + r.step - 1) / r.step);
+        if (even_marks) {
+            const uint32_t step = (uint32_t)(((r.cap + even_marks - 1) / even_marks + 511) & ~(uint64_t)511);
+            for (uint64_t e = step; e < r.cap; e += step) r.at[r.marks++] = (uint32_t)e;
+        } else {
+            static const uint32_t num[6] = {8, 16, 24, 28, 30, 31};  // 32nds of a row
+            for (uint32_t k = 0; k < 6; k++) {
+                const uint32_t e = (uint32_t)((r.cap * num[k] / 32) & ~(uint64_t)511);
+                if (e > (r.marks ? r.at[r.marks - 1] : 0u) && e < r.cap) r.at[r.marks++] = e;
+            }
+        }
+        r.at[r.marks++] = (uint32_t)r.cap;
         pending_marks += r.marks;
         rows[c] = r;
     }
@@ -363,14 +379,16 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
     auto copy_mark = [&](uint32_t c, uint32_t m) {  // output columns [m * step, (m + 1) * step) of every row of chunk c
         const Rows& r = rows[c];
         const uint32_t s0 = first[c], cnt = first[c + 1] - s0;
-        const uint64_t col = (uint64_t)m * r.step;
-        const uint64_t width = r.cap - col < r.step ? r.cap - col : r.step;
+        const uint64_t col = m ? r.at[m - 1] : 0;
+        const uint64_t width = r.at[m] - col;
         return cudaMemcpy2DAsync(out + out_off[s0] + col, r.pitch, d_out + (out_off[s0] - so.lo) + col, r.pitch, width, cnt,
                                  cudaMemcpyDeviceToHost, d->copy_out);
     };
 
-    CUDA_TRY(d->ctrl.reserve(64 * sizeof(uint32_t)));
-    CUDA_TRY(cudaMemsetAsync(d->ctrl.p, 0, 64 * sizeof(uint32_t), st));
+    // ctrl: [0, 16) the chunks' tickets, [64, 64 + 16 * kMaxMarks) their device-side progress counters
+    const size_t ctrl_words = 64 + 16 * (size_t)kMaxMarks;
+    CUDA_TRY(d->ctrl.reserve(ctrl_words * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemsetAsync(d->ctrl.p, 0, ctrl_words * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemcpyAsync(dm, hm, (size_t)n * 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     cudaEvent_t ready, ev_in[16], ev_k[16];
     uint32_t n_events = 0;
@@ -396,7 +414,7 @@ int lzb_dec_code_batch(lzb_dec* d, const uint8_t* in, const uint64_t* in_off, co
         rc = dec_enqueue(d, d_in, dm + s0, dm + n + s0, cnt, d_out, dm + 2 * (size_t)n + s0, dm + 3 * (size_t)n + s0,
                          dm + 4 * (size_t)n + s0, (int32_t*)(dm + 5 * (size_t)n) + s0, max_lclp1, max_pb1, mode,
                          (uint32_t*)d->ctrl.p + c, ks, c % n_k, n_k, rows[c].on ? (uint32_t*)d->h_progress.p + c * kMarks : nullptr,
-                         rows[c].marks, rows[c].step);
+                         (uint32_t*)d->ctrl.p + 64 + c * kMaxMarks, rows[c].marks, rows[c].at);
         if (rc != LZB_OK) break;
         cudaEventRecord(ev_k[c], ks);
         cudaStreamWaitEvent(st, ev_k[c], 0);  // the out_len / status read-back below follows every kernel

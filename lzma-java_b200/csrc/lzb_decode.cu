@@ -423,13 +423,24 @@ __device__ __forceinline__ uint32_t decode_literal_g(RD& rd, uint16_t* probs, bo
 
 enum : int { EV_MATCH = 0, EV_DONE = 1, EV_DATA_ERROR = 2, EV_CAPACITY = 3 };
 
-// DecodeArgs::progress: every lane publishes its own output stores system-wide, then lane 0 counts
-// the stream in for marks [from, to).
+// DecodeArgs::progress, marks [from, to) of one stream.  Lane 0 publishes the warp's output stores at device
+// scope (__syncwarp orders every lane's stores before its fence, which is cumulative) and counts the stream
+// in a device-memory counter per mark; the stream that completes a mark -- it has then observed every other
+// stream's count, hence their stores -- publishes system-wide and tells the host.  The host only ever starts
+// a DMA read of the output after it has seen progress[m] = n.
 __device__ __forceinline__ void report_progress(const DecodeArgs& a, uint32_t from, uint32_t to, int lane) {
-    __threadfence_system();
     __syncwarp();
-    if (lane == 0)
-        for (uint32_t m = from; m < to; m++) atomicAdd_system(a.progress + m, 1u);
+    if (lane == 0 && from < to) {
+        __threadfence();
+        uint32_t full = 0;  // marks (at most kDecMaxMarks = 32) that this stream completed for the whole batch
+        for (uint32_t m = from; m < to; m++)
+            if (atomicAdd(a.progress_dev + m, 1u) == a.n - 1) full |= 1u << m;
+        if (full) {
+            __threadfence_system();
+            for (uint32_t m = from; m < to; m++)
+                if (full >> m & 1u) *reinterpret_cast<volatile uint32_t*>(a.progress + m) = a.n;
+        }
+    }
 }
 
 template <int MODE, bool PROGRESS>
@@ -443,7 +454,7 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
     int status = 1;
     uint32_t pos = 0;
     uint32_t marks_done = 0;  // progress marks already reported for this stream
-    uint32_t next_mark = PROGRESS && a.marks > 1 ? a.mark_step : 0xFFFFFFFFu;  // output position of the next mark to report
+    uint32_t next_mark = PROGRESS && a.marks > 1 ? a.mark_at[0] : 0xFFFFFFFFu;  // output position of the next mark to report
     if (in_len < LZB_KERNEL_HEADER) {
         status = 0;  // "input .lzma file is too short" / "Can't read stream size"
     } else if (in_len - LZB_KERNEL_HEADER >= 0xFFFFFFF0ull || cap64 >= 0xFFFFFFF0ull) {
@@ -599,11 +610,11 @@ __device__ void decode_stream(const DecodeArgs& a, uint32_t s, uint16_t* model, 
                 pos = __shfl_sync(kFull, pos, 0);
                 if (PROGRESS && (evlen >> 31)) {
                     // everything below `pos` is stored (the pending tail went out above)
-                    uint32_t reached = pos / a.mark_step;
-                    if (reached > a.marks - 1) reached = a.marks - 1;
+                    uint32_t reached = marks_done;
+                    while (reached + 1 < a.marks && a.mark_at[reached] <= pos) reached++;
                     report_progress(a, marks_done, reached, lane);
                     marks_done = reached;
-                    next_mark = marks_done + 1 < a.marks ? (marks_done + 1) * a.mark_step : 0xFFFFFFFFu;
+                    next_mark = marks_done + 1 < a.marks ? a.mark_at[marks_done] : 0xFFFFFFFFu;
                 }
                 __syncwarp();  // order earlier stores (lane 0's literals, other lanes' copies) before these loads
                 const uint8_t* src = out + pos - d;
