@@ -458,7 +458,7 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
         if (err != cudaSuccess) return err;
         err = launch_mf(w, (uint32_t)a.max_in_len, num_sms, S[k], a.tune_timing ? f.mev + 1 : nullptr);
         if (err != cudaSuccess) return err;
-        nl += a.max_in_len ? 3 : 1;
+        nl += a.max_in_len ? 4 : 2;
         err = launch_list_scan(w, (uint32_t)a.max_in_len, f.G.tile_sum, f.G.w_total, S[k]);
         if (err != cudaSuccess) return err;
         nl += a.max_in_len ? 2 : 1;

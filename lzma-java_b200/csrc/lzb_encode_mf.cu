@@ -66,6 +66,12 @@ struct LinkStep {
     }
 };
 
+// one thread per block: a block longer than the declared max_in_len would overflow its scratch slices
+__global__ void __launch_bounds__(256) lzb_mf_check_lengths(MfWave w) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < w.n_blocks && w.in_len[b] > (uint64_t)w.np - 1) atomicMax(w.overflow, 2u);
+}
+
 __global__ void __launch_bounds__(128) lzb_mf_link_kernel(MfWave w) {
     __shared__ uint32_t s_crc[256];  // constant memory would serialise the 32 different indices of a warp
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = c_crc[i];
@@ -74,11 +80,11 @@ __global__ void __launch_bounds__(128) lzb_mf_link_kernel(MfWave w) {
     const int lane = threadIdx.x & 31;
     if (b >= w.n_blocks) return;
     const uint8_t* data = w.in + w.in_off[b];
-    if (w.in_len[b] > (uint64_t)w.np - 1) {  // longer than the caller's max_in_len: the scratch slices would overflow
-        if (lane == 0) atomicMax(w.overflow, 2u);
-        return;
-    }
-    const uint32_t n = (uint32_t)w.in_len[b];
+    // A block longer than the caller's max_in_len is flagged by lzb_mf_check_lengths and the host gives up on the
+    // batch; here it is merely cut to what its scratch slices hold.  (The check used to sit in this kernel as an
+    // early return: 2048 x 1 MiB blocks then took 0.72 s instead of 0.24 s, measured by removing just that.)
+    const uint64_t len64 = w.in_len[b];
+    const uint32_t n = len64 > (uint64_t)w.np - 1 ? w.np - 1 : (uint32_t)len64;
     uint32_t* heads = w.heads + (size_t)b * w.hash_stride;
     uint32_t* next = w.next + (size_t)b * w.np;
     uint32_t* prev2 = w.prev2 + (size_t)b * w.np;
@@ -617,6 +623,7 @@ cudaError_t launch_list_gather(const MfWave& w, uint32_t max_len, const uint32_t
 cudaError_t launch_mf(const MfWave& w, uint32_t max_len, int num_sms, cudaStream_t st, cudaEvent_t* ev) {
     if (w.n_blocks == 0) return cudaSuccess;
     const uint32_t warps_per_cta = 4;
+    lzb_mf_check_lengths<<<(w.n_blocks + 255) / 256, 256, 0, st>>>(w);
     lzb_mf_link_kernel<<<(w.n_blocks + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, st>>>(w);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
