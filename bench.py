@@ -48,8 +48,8 @@ ENC = dict(size=1 << 20, dict_size=1 << 20, fb=64, cls=4, config_id=3)     # con
 C5 = dict(size=4 << 20, dict_size=1 << 22, fb=32, cls=4, config_id=5, blocks=2048)  # configs[4]
 METRIC = "LZMA batch decode, uncompressed input MB/s (bit-exact vs reference)"
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the bench shape (profiles/, one ncu --set full capture each)
-NCU_DRAM_BYTES_DECODE = 8.123094e9 + 1.182275e9   # profiles/r01_decode_hybrid_ncu.txt, 4096 x 256 KiB text streams
-NCU_DRAM_BYTES_PARSE_PER_INPUT_BYTE = (59.671165e9 + 1.956729e9) / (2072 * 131072)  # profiles/r02_parse_w14_ncu.txt
+NCU_DRAM_BYTES_DECODE = 8.091469e9 + 1.174024e9   # profiles/r02_decode_hybrid_ncu.txt, 4096 x 256 KiB text streams
+NCU_DRAM_BYTES_PARSE_PER_INPUT_BYTE = (6.117494e9 + 0.684309e9) / (2072 * 131072)  # profiles/r02_parse_full14_ncu.txt (lists position-ordered)
 
 
 def hbm_peak():
@@ -397,7 +397,7 @@ def run_b200(args, rank, world, local_rank):
             "gpu_launches": int(timed_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_DECODE if n == 4096 else None,
-                         "traffic_source": "profiles/r01_decode_hybrid_ncu.txt (dram__bytes_read+write, one ncu --set full capture of this launch shape)",
+                         "traffic_source": "profiles/r02_decode_hybrid_ncu.txt (dram__bytes_read+write, one ncu --set full capture of this launch shape)",
                          "peak_source": peak_src, "kernel": "lzb_decode_kernel<kDecHybrid>",
                          "algorithmic_bytes_per_launch": n * size + total_c, "kernel_ms": kernel_ms,
                          "note": "serial range-decoder chains: issue/latency bound, not HBM bound (profiles/)"},
@@ -485,7 +485,7 @@ def bench_encode(args, lzb, torch, corpus, dev, stream, rank, world, threads, R,
            "gpu_launches": int(launches),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": NCU_DRAM_BYTES_PARSE_PER_INPUT_BYTE * n * size,
-                        "traffic_source": "profiles/r02_parse_w14_ncu.txt: dram bytes of lzb_parse_kernel per input byte "
+                        "traffic_source": "profiles/r02_parse_full14_ncu.txt: dram bytes of lzb_parse_kernel per input byte "
                                           "(2072 x 128 KiB of this corpus mix), scaled to this launch",
                         "kernel": "lzb_parse_kernel (dominant), lzb_mf_long_kernel, lzb_mf_tree_kernel, lzb_mf_link_kernel"},
            "compressed_ratio": total_c / (n * size),

@@ -336,7 +336,14 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
         return carve_group(nullptr, gb, P.np, P.hash_stride, pair_cap_for(pm, a.max_in_len), nullptr, nullptr, nullptr);
     };
     uint32_t gmax = std::min<uint32_t>(a.n, 32768);
-    const size_t group_budget = std::max<size_t>((budget - std::min(budget, fixed_bytes)) / 20 * 9 / (size_t)K, group_bytes(1, pair_mul));
+    // the groups get 45 % of the budget, or whatever the list pool is not expected to need if that is more (the match
+    // finder's time goes with the number of rounds: 2048 x 1 MiB in 2 rounds of 6 x 171 instead of 3 of 6 x 114)
+    const uint64_t pool_per_block = pool_need(a.max_in_len, (uint64_t)(4.5 * (double)a.max_in_len));
+    const uint64_t pool_expect = std::min<uint64_t>((uint64_t)a.n * pool_per_block, (uint64_t)1 << 46);
+    const size_t avail = budget - std::min(budget, fixed_bytes);
+    size_t groups_total = avail / 20 * 9;
+    if (!mf_only && avail > pool_expect) groups_total = std::min<size_t>(std::max<size_t>(groups_total, avail - (size_t)pool_expect), avail / 10 * 7);
+    const size_t group_budget = std::max<size_t>(groups_total / (size_t)K, group_bytes(1, pair_mul));
     if (group_bytes(gmax, pair_mul) > group_budget) {
         uint32_t lo = 1, hi = gmax;  // group_bytes is monotonic: binary search the largest count that fits
         while (lo < hi) {
@@ -358,8 +365,7 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
     // per byte), bounded by what the budget leaves; a wave ends when the next group does not fit
     size_t pool_cap = scratch.pool_cap;
     if (!mf_only) {
-        const uint64_t per_block = pool_need(a.max_in_len, (uint64_t)(4.5 * (double)a.max_in_len));
-        const uint64_t expect = std::min<uint64_t>((uint64_t)a.n * per_block, (uint64_t)1 << 46);
+        const uint64_t expect = pool_expect;
         const size_t gbytes = (size_t)K * group_bytes(gmax, pair_mul);
         const size_t room = budget > fixed_bytes + gbytes ? budget - fixed_bytes - gbytes : 0;
         size_t want = (size_t)std::min<uint64_t>(expect, room);
