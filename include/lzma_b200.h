@@ -91,6 +91,18 @@ int lzb_enc_write_coder_properties(const lzb_enc *e, uint8_t out[5]);
  * (in_len + in_len/3 + 128; add LZB_HEADER_SIZE when with_header13). */
 uint64_t lzb_enc_bound(uint64_t in_len);
 
+/* The ICodeProgress argument of Encoder.Code (ICodeProgress.java:3-5,
+ * Encoder.java:929-933, 1070-1072: SetProgress(processedInSize,
+ * processedOutSize) after every CodeOneBlock, i.e. every >= 4096 input
+ * bytes).  While a later lzb_enc_code* call of this handle runs, `fn` is
+ * called from the calling thread with the call's running totals (input bytes
+ * consumed, output bytes produced incl. the range coder's pending bytes, as
+ * RangeEncoder.getProcessedSizeAdd), monotonically, about once per 64 KiB
+ * consumed by a stream while the parser runs (the match finder's phase
+ * reports nothing: it produces no output).  fn = NULL switches it off. */
+typedef void (*lzb_progress_fn)(void *user, uint64_t in_size, uint64_t out_size);
+int lzb_enc_set_progress(lzb_enc *e, lzb_progress_fn fn, void *user);
+
 /* Encoder.Code (Encoder.java:1064-1077) for one stream held in host memory:
  * `in` is what the reference would have drained from its InputStream, `out`
  * receives what it would have written to its OutputStream (payload only, no

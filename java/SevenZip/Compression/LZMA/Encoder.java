@@ -120,7 +120,23 @@ public class Encoder implements AutoCloseable {
             out = LzmaB200.pinned(cap);
             MemorySegment.copy(data, 0, in, JAVA_BYTE, 0, data.length);
             final MemorySegment outLen = arena.allocate(JAVA_LONG);
-            final int rc = (int) LzmaB200.ENC_CODE.invokeExact(handle, in, (long) data.length, out, cap, outLen);
+            if (progress != null) {
+                // ICodeProgress as an upcall: the library calls it from this thread with running totals while the parser
+                // runs (Encoder.java:929-933, 1070-1072 call it after every CodeOneBlock)
+                final java.lang.invoke.MethodHandle target = java.lang.invoke.MethodHandles.lookup().bind(
+                        new ProgressUpcall(progress), "call",
+                        java.lang.invoke.MethodType.methodType(void.class, MemorySegment.class, long.class, long.class));
+                final MemorySegment stub = LzmaB200.LINKER.upcallStub(target, LzmaB200.PROGRESS_FD, arena);
+                ok((int) LzmaB200.ENC_SET_PROGRESS.invokeExact(handle, stub, MemorySegment.NULL));
+            }
+            final int rc;
+            try {
+                rc = (int) LzmaB200.ENC_CODE.invokeExact(handle, in, (long) data.length, out, cap, outLen);
+            } finally {
+                if (progress != null) {
+                    ok((int) LzmaB200.ENC_SET_PROGRESS.invokeExact(handle, MemorySegment.NULL, MemorySegment.NULL));
+                }
+            }
             if (rc != LzmaB200.OK) {
                 throw new IOException("lzb_enc_code (" + rc + "): " + LzmaB200.lastError());
             }
@@ -146,6 +162,20 @@ public class Encoder implements AutoCloseable {
             if (out != null) {
                 LzmaB200.free(out);
             }
+        }
+    }
+
+    /** Receiver of the lzb_progress_fn upcall. */
+    private static final class ProgressUpcall {
+        private final ICodeProgress progress;
+
+        ProgressUpcall(ICodeProgress progress) {
+            this.progress = progress;
+        }
+
+        @SuppressWarnings("unused")  // bound by name in Code
+        void call(MemorySegment user, long inSize, long outSize) {
+            progress.SetProgress(inSize, outSize);
         }
     }
 

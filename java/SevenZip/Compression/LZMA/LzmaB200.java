@@ -25,7 +25,7 @@ final class LzmaB200 {
 
     static final int OK = 1;
 
-    private static final Linker LINKER = Linker.nativeLinker();
+    static final Linker LINKER = Linker.nativeLinker();
     private static final SymbolLookup LIB = open();
 
     private static SymbolLookup open() {
@@ -54,6 +54,9 @@ final class LzmaB200 {
     static final MethodHandle ENC_SET_LCLPPB = fn("lzb_enc_set_lc_lp_pb", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT));
     static final MethodHandle ENC_SET_EOS = fn("lzb_enc_set_end_marker_mode", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
     static final MethodHandle ENC_PROPS = fn("lzb_enc_write_coder_properties", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle ENC_SET_PROGRESS = fn("lzb_enc_set_progress", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    /** lzb_progress_fn: void (*)(void *user, uint64_t in_size, uint64_t out_size) */
+    static final FunctionDescriptor PROGRESS_FD = FunctionDescriptor.ofVoid(ADDRESS, JAVA_LONG, JAVA_LONG);
     static final MethodHandle ENC_CODE = fn("lzb_enc_code",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG, ADDRESS));
 

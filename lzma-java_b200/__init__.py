@@ -31,6 +31,7 @@ LZB_E_CAPACITY = -4
 LZB_E_UNSUPPORTED = -5
 HEADER_SIZE = 13
 
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.c_uint64)  # lzb_progress_fn
 # every symbol include/lzma_b200.h declares: (name, restype, argtypes)
 _vp, _u8p, _u64p, _i32p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
 ABI = [
@@ -50,6 +51,7 @@ ABI = [
     ("lzb_enc_set_algorithm", C.c_int, [C.c_int32]),
     ("lzb_enc_write_coder_properties", C.c_int, [_vp, _u8p]),
     ("lzb_enc_bound", C.c_uint64, [C.c_uint64]),
+    ("lzb_enc_set_progress", C.c_int, [_vp, _vp, _vp]),
     ("lzb_enc_code", C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_uint64, _u64p]),
     ("lzb_enc_code_batch", C.c_int, [_vp, _u8p, _u64p, _u64p, C.c_uint32, _u8p, _u64p, _u64p, _u64p, C.c_int32]),
     ("lzb_enc_code_batch_device", C.c_int,
@@ -164,9 +166,19 @@ class Encoder:
     def Code(self, inStream, outStream, inSize=-1, outSize=-1, progress=None):
         """Encoder.Code (Encoder.java:1064): drains inStream, writes the payload
         (no header) to outStream.  inSize/outSize are ignored like in the
-        reference; progress.SetProgress(in, out) is called once at the end."""
+        reference.  progress.SetProgress(in, out) (ICodeProgress.java:3-5) is called with
+        monotone running totals while the parser runs (about every 64 KiB; the reference: every
+        >= 4096 bytes, Encoder.java:929-933) and once more with the final sizes."""
         data = inStream.read()
-        payload = self.code_bytes(data)
+        if progress is None:
+            payload = self.code_bytes(data)
+        else:
+            cb = PROGRESS_FN(lambda _user, n_in, n_out: progress.SetProgress(n_in, n_out))
+            _check(lib().lzb_enc_set_progress(self._h, C.cast(cb, C.c_void_p), None))
+            try:
+                payload = self.code_bytes(data)
+            finally:
+                _check(lib().lzb_enc_set_progress(self._h, None, None))
         outStream.write(payload)
         if progress is not None:
             progress.SetProgress(len(data), len(payload))

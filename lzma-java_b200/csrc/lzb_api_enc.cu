@@ -29,6 +29,8 @@ struct lzb_enc {
     int32_t tune_warps = 0, tune_pair_mul = 0, tune_lit = -1, tune_group = 0, tune_inflight = 0;
     int64_t tune_pool = 0;
     bool tune_fifo = false, tune_timing = false, tune_blocked = false;
+    lzb_progress_fn progress_fn = nullptr;  // ICodeProgress of the next Code calls
+    void* progress_user = nullptr;
 };
 
 extern "C" {
@@ -110,6 +112,13 @@ int lzb_enc_write_coder_properties(const lzb_enc* e, uint8_t out[5]) {  // :1079
 
 uint64_t lzb_enc_bound(uint64_t in_len) { return in_len + in_len / 3 + 128; }
 
+int lzb_enc_set_progress(lzb_enc* e, lzb_progress_fn fn, void* user) {  // the ICodeProgress argument of Encoder.Code (:1064)
+    if (!e) return fail(LZB_E_ARG, "null handle");
+    e->progress_fn = fn;
+    e->progress_user = user;
+    return LZB_OK;
+}
+
 int lzb_enc_code_batch_device(lzb_enc* e, const uint8_t* d_in, const uint64_t* d_in_off, const uint64_t* d_in_len,
                               uint32_t n, uint64_t max_in_len, uint8_t* d_out, const uint64_t* d_out_off,
                               const uint64_t* d_out_cap, uint64_t* d_out_len, int32_t with_header13,
@@ -142,6 +151,8 @@ int lzb_enc_code_batch_device(lzb_enc* e, const uint8_t* d_in, const uint64_t* d
     a.pb = e->pb;
     a.eos = e->eos;
     a.with_header = with_header13 != 0;
+    a.progress_fn = e->progress_fn;
+    a.progress_user = e->progress_user;
     a.tune_warps = e->tune_warps;
     a.tune_pair_mul = e->tune_pair_mul;
     a.tune_lit = e->tune_lit;

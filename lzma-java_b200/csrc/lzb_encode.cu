@@ -13,6 +13,8 @@
 // and the scratch is reused.  A wave is every group that fits the pool: the parser then sees as many blocks
 // at once as possible, handed out longest-expected-first, so that its slots stay busy to the end.
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -168,7 +170,7 @@ struct Wave {
 };
 
 cudaError_t parse_wave(const EncodeArgs& a, const Plan& P, const Fixed& F, const uint8_t* pool, Wave& wv, int num_sms, cudaStream_t st,
-                       int* nl) {
+                       int* nl, unsigned long long* h_progress) {
     const uint32_t wb = (uint32_t)wv.lists.size();
     if (wb == 0) return cudaSuccess;
     cudaError_t e;
@@ -196,6 +198,7 @@ cudaError_t parse_wave(const EncodeArgs& a, const Plan& P, const Fixed& F, const
     pa.with_header = a.with_header;
     pa.slice_bytes = P.geo.slice_bytes;
     pa.lit_in_smem = P.geo.lit_in_smem;
+    pa.progress = a.progress_fn ? h_progress : nullptr;
     e = cudaMemsetAsync(F.ticket, 0, 64 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyAsync(F.lists, wv.lists.data(), (size_t)wb * sizeof(BlockLists), cudaMemcpyHostToDevice, st);
@@ -249,6 +252,19 @@ cudaError_t parse_wave(const EncodeArgs& a, const Plan& P, const Fixed& F, const
     if (e != cudaSuccess) return e;
     *nl += 1;
     if (a.tune_timing) cudaEventRecord(t1, st);
+    if (a.progress_fn && h_progress) {
+        // ICodeProgress: the streams add to two counters in pinned memory; report them while the kernel runs
+        volatile unsigned long long* hp = h_progress;
+        unsigned long long seen = hp[0];
+        while (cudaStreamQuery(st) == cudaErrorNotReady) {
+            const unsigned long long in_now = hp[0], out_now = hp[1];
+            if (in_now != seen) {
+                seen = in_now;
+                a.progress_fn(a.progress_user, in_now, out_now);
+            }
+            std::this_thread::sleep_for(std::chrono::microseconds(200));
+        }
+    }
     // the host vectors above are pageable and die with this scope; the pool is reused by the next wave
     e = cudaStreamSynchronize(st);
     if (a.tune_timing) {
@@ -282,6 +298,8 @@ void EncScratch::release() {
     if (pool) cudaFree(pool);
     if (fixed) cudaFree(fixed);
     if (h_totals) cudaFreeHost(h_totals);
+    if (h_progress) cudaFreeHost(h_progress);
+    h_progress = nullptr;
     pool = fixed = nullptr;
     h_totals = nullptr;
     pool_cap = fixed_cap = h_totals_cap = 0;
@@ -295,6 +313,13 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
     cudaError_t e = upload_mf_tables();
     if (e != cudaSuccess) return e;
 
+    if (a.progress_fn) {
+        if (!scratch.h_progress) {
+            e = cudaHostAlloc((void**)&scratch.h_progress, 2 * sizeof(unsigned long long), cudaHostAllocMapped);
+            if (e != cudaSuccess) return e;
+        }
+        scratch.h_progress[0] = scratch.h_progress[1] = 0;
+    }
     Plan P;
     P.hash_stride = hash_stride_for(a.dict_size, a.bt4, &P.hash_mask);
     P.np = (uint32_t)a.max_in_len + 1;
@@ -544,7 +569,7 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
             if (wv.pool_used + need > pool_cap && !wv.lists.empty()) {
                 e = sync_all();  // every gather into the pool has finished (and the groups in flight, early)
                 if (e != cudaSuccess) return e;
-                e = parse_wave(a, P, F, pool, wv, num_sms, st, &nl);
+                e = parse_wave(a, P, F, pool, wv, num_sms, st, &nl, scratch.h_progress);
                 if (e != cudaSuccess) return e;
             }
             if (need > scratch.pool_cap) {  // one group alone is larger than the pool: enlarge it (nothing is parked in it now)
@@ -581,7 +606,7 @@ cudaError_t run_encode(const EncodeArgs& a, EncScratch& scratch, int num_sms, cu
     }
     e = sync_all();
     if (e != cudaSuccess) return e;
-    e = parse_wave(a, P, F, pool, wv, num_sms, st, &nl);
+    e = parse_wave(a, P, F, pool, wv, num_sms, st, &nl, scratch.h_progress);
     if (launches) *launches = nl;
     return e;
 }

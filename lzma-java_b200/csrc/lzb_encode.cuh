@@ -105,7 +105,11 @@ struct ParseArgs {
     bool eos, with_header;
     uint32_t slice_bytes;    // shared memory per warp
     bool lit_in_smem;        // literal coders in the warp's slice (else in lit_scratch)
+    // ICodeProgress (Encoder.java:929-933, 1070-1072): when set, every stream adds what it has consumed / produced
+    // to progress[0] / progress[1] (pinned host memory) each time it has advanced by kProgressStep input bytes
+    unsigned long long* progress;
 };
+constexpr uint32_t kProgressStep = 1u << 16;
 
 struct ParseGeometry {
     uint32_t slice_bytes, cta_table_bytes;

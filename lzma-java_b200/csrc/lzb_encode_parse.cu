@@ -208,6 +208,8 @@ struct __align__(16) WarpCtx {
     int32_t* len_counters;
     int32_t pb, table_size, dist_table_size;
     int32_t off_len, off_rep_len, off_pos_slot, off_pos_dec, off_pos_align;
+    unsigned long long* progress;         // ParseArgs::progress (null: nobody listens)
+    uint32_t progress_in, progress_out;   // what this stream has reported so far
 };
 
 // ---- shared-memory slice of one warp ----------------------------------------
@@ -372,6 +374,22 @@ __device__ __noinline__ void ctx_fill_align_prices(const WarpCtx* c, int lane) {
     __syncwarp();
 }
 
+// ICodeProgress.SetProgress(nowPos64, rangeEncoder.getProcessedSizeAdd()) of Encoder.java:922-923, 1070-1072, as deltas
+// added to the call's totals in pinned host memory; informational, so no fence.  Out of line and on values only: it runs
+// once per kProgressStep input bytes.  Returns the position of the next report.
+__device__ __noinline__ uint32_t ctx_report_progress(WarpCtx* c, uint32_t now_pos, int lane) {
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t produced = c->rc.pos + c->rc.cache_size + 4;  // RangeEncoder.java:69-71
+        atomicAdd_system(c->progress, (unsigned long long)(now_pos - c->progress_in));
+        atomicAdd_system(c->progress + 1, (unsigned long long)(produced - c->progress_out));
+        c->progress_in = now_pos;
+        c->progress_out = produced;
+    }
+    __syncwarp();
+    return now_pos + kProgressStep;
+}
+
 // ---- everything one stream needs (identical in every lane unless noted) -----
 struct Enc {
     const CtaTables* T;
@@ -412,6 +430,7 @@ struct Enc {
     int longest_len;
     int match_price_count, align_price_count;
     uint32_t now_pos;
+    uint32_t progress_next;  // input position of the next ICodeProgress report (0xFFFFFFFF: nobody listens)
 
     // ---- prices (ProbPrices.java:23-37) ----
     __device__ __forceinline__ uint32_t price_bit(uint32_t prob, uint32_t bit) const {
@@ -743,8 +762,8 @@ struct Enc {
 
     __device__ __forceinline__ int get_optimum(uint32_t position, uint32_t* back_out);
     __device__ __forceinline__ void emit_match(uint32_t ps, int len, uint32_t pos, int slot);
-    __device__ __forceinline__ bool encode_one(bool finish);
-    __device__ __forceinline__ void run();
+    template <bool PROGRESS> __device__ __forceinline__ bool encode_one(bool finish);
+    template <bool PROGRESS> __device__ __forceinline__ void run();
 };
 
 // getOptimum (Encoder.java:364-811).  Returns the length, *back_out = "pos" of PosAndLength
@@ -1227,6 +1246,7 @@ __device__ __forceinline__ void Enc::emit_match(uint32_t ps, int len, uint32_t p
 // encodeOne (:890-936) with its emitters (:938-1024); false once the input is used up.  With
 // `finish` it emits the end marker instead (WriteEndMarker :818-835: the match symbol with len 2,
 // posSlot 63 and an all-ones 32-bit "distance"), through the same emission code as every match.
+template <bool PROGRESS>
 __device__ __forceinline__ bool Enc::encode_one(bool finish) {
     uint32_t back = kNumRepDistances;
     int len = kMatchMinLen;
@@ -1297,6 +1317,7 @@ __device__ __forceinline__ bool Enc::encode_one(bool finish) {
     }
     additional_offset -= len;
     now_pos += len;
+    if (PROGRESS && now_pos >= progress_next) progress_next = ctx_report_progress(ctx, now_pos, lane);
     if (additional_offset == 0) {
         if (match_price_count >= (1 << 7)) fill_distances_prices();
         if (align_price_count >= kAlignTableSize) fill_align_prices();
@@ -1306,6 +1327,7 @@ __device__ __forceinline__ bool Enc::encode_one(bool finish) {
 }
 
 // SetStreams + CodeOneBlock loop (Encoder.java:1046-1077, 843-888); probabilities already initialised
+template <bool PROGRESS>
 __device__ __forceinline__ void Enc::run() {
     state = 0;
     prev_byte = 0;
@@ -1320,6 +1342,7 @@ __device__ __forceinline__ void Enc::run() {
     pf_off = kMfEmpty;
     pf_cnt = pf_pair = pf_l2 = pf_from = 0;
     now_pos = 0;
+    progress_next = ctx->progress ? kProgressStep : 0xFFFFFFFFu;
     num_pairs = 0;
     match_price_count = 0;
     align_price_count = 0;
@@ -1350,8 +1373,8 @@ __device__ __forceinline__ void Enc::run() {
         more = avail() != 0;
     }
     #pragma unroll 1
-    while (more) more = encode_one(false);
-    if (eos) encode_one(true);  // Flush (:837-841): the end marker if asked for ...
+    while (more) more = encode_one<PROGRESS>(false);
+    if (eos) encode_one<PROGRESS>(true);  // Flush (:837-841): the end marker if asked for ...
     rc_flush(&ctx->rc, lane);   // ... and five shiftLow
 }
 
@@ -1359,7 +1382,7 @@ __device__ __forceinline__ void Enc::run() {
 // kEncWarpsLitSmem streams per SM with the literal coders in shared memory (168 registers), and up
 // to kEncMaxWarps with the literal coders in global memory (L2), which is what lets a wave with more
 // blocks than the first variant's slots keep 12-14 serial chains per SM in flight.
-template <int MAXW>
+template <int MAXW, bool PROGRESS>
 __global__ void __launch_bounds__(MAXW * 32, 1) lzb_parse_kernel(ParseArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CtaTables* tables = reinterpret_cast<CtaTables*>(smem_raw);
@@ -1438,6 +1461,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) lzb_parse_kernel(ParseArgs a) {
         }
         __syncwarp();
         rc_init(&ctx->rc, out, cap, lane);
+        if (lane == 0) {
+            ctx->progress = a.progress;
+            ctx->progress_in = ctx->progress_out = 0;
+        }
+        __syncwarp();
         Enc e;
         e.T = tables;
         e.model = model;
@@ -1471,7 +1499,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) lzb_parse_kernel(ParseArgs a) {
         e.pos_mask = (1u << a.pb) - 1;
         e.lp_mask = (1u << a.lp) - 1;
         e.eos = a.eos;
-        e.run();
+        e.run<PROGRESS>();
         if (lane == 0) a.out_len[b] = (uint64_t)ctx->rc.pos > cap ? ~0ull : (uint64_t)ctx->rc.pos + header;
         __syncwarp();
         (void)ticket_b;
@@ -1514,7 +1542,10 @@ size_t parse_opt_bytes_per_slot() { return sizeof(OptNode) * (size_t)kNumOpts; }
 
 cudaError_t launch_parse(const ParseArgs& a, int grid, int warps, cudaStream_t st) {
     const size_t smem = sizeof(CtaTables) + (size_t)warps * a.slice_bytes;
-    auto kern = a.lit_in_smem ? lzb_parse_kernel<kEncWarpsLitSmem> : lzb_parse_kernel<kEncMaxWarps>;
+    // four instances: where the literal coders live x whether anybody listens to ICodeProgress (the test for the
+    // next report sits in the symbol loop: two instructions and a register that cost 3 % on C3 when compiled in)
+    auto kern = a.lit_in_smem ? (a.progress ? lzb_parse_kernel<kEncWarpsLitSmem, true> : lzb_parse_kernel<kEncWarpsLitSmem, false>)
+                              : (a.progress ? lzb_parse_kernel<kEncMaxWarps, true> : lzb_parse_kernel<kEncMaxWarps, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     kern<<<grid, warps * 32, smem, st>>>(a);

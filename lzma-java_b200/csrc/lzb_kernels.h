@@ -79,6 +79,9 @@ struct EncodeArgs {
     bool bt4;
     int32_t lc, lp, pb;
     bool eos, with_header;
+    // ICodeProgress: called from the calling thread while the parser runs, with batch totals (in, out); may be null
+    void (*progress_fn)(void* user, uint64_t in_size, uint64_t out_size) = nullptr;
+    void* progress_user = nullptr;
     // developer / test hooks, read once when the handle is created (lzb_enc_create)
     int32_t tune_warps = 0;      // LZB_ENC_WARPS: parser streams per SM (0 = automatic)
     int32_t tune_pair_mul = 0;   // LZB_PAIR_MUL: initial match-pair budget in slots per input byte (0 = default)
@@ -107,6 +110,7 @@ struct EncScratch {
     size_t pool_cap = 0;
     void* fixed = nullptr;
     size_t fixed_cap = 0;
+    unsigned long long* h_progress = nullptr;  // pinned: (in, out) totals of the call in flight
     void release();
 };
 

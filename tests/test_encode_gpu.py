@@ -117,6 +117,34 @@ def test_encode_payload_only_and_class_api(lzb, oracle, corpus):
     assert pr.calls and pr.calls[-1][0] >= len(data)  # LzmaBench.java:219-223,366-368
 
 
+def test_encode_reports_progress_while_it_runs(lzb, oracle, corpus):
+    """ICodeProgress (ICodeProgress.java:3-5; Encoder.java:929-933, 1070-1072 call it after every CodeOneBlock):
+    running totals arrive while the stream is being coded, monotone in both sizes, bounded by the final ones, and
+    the bytes are still the oracle's."""
+    data = corpus.generate(1 << 20, 1, corpus.TEXT, 41).tobytes()
+
+    class Progress:
+        def __init__(self):
+            self.calls = []
+
+        def SetProgress(self, a, b):
+            self.calls.append((a, b))
+
+    pr = Progress()
+    enc = _encoder(lzb, BASE)
+    payload = io.BytesIO()
+    enc.Code(io.BytesIO(data), payload, -1, -1, pr)
+    enc.close()
+    ref = oracle.encode(data, oracle.props(**BASE))
+    assert payload.getvalue() == ref
+    assert pr.calls[-1] == (len(data), len(ref))
+    running = pr.calls[:-1]
+    assert len(running) >= 4, running  # 16 reports of 64 KiB leave the kernel; the host polls every 200 us
+    assert all(0 < a <= len(data) for a, _ in running)
+    assert all(x[0] < y[0] and x[1] <= y[1] for x, y in zip(running, running[1:]))
+    assert all(0 < b <= len(ref) + 5 for _, b in running)  # getProcessedSizeAdd counts the coder's 5 pending bytes
+
+
 def test_encode_1mib_blocks_c3(lzb, oracle, corpus):
     """BASELINE config 3 shape: 1 MiB blocks, dict 1 MiB, fb 64, mixed corpus (8 blocks here)."""
     p = dict(BASE)
