@@ -798,7 +798,7 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
 
     // window bytes and the four rep comparisons, 32 bytes at once (:393-399, limit 273)
     uint32_t c = m - 1;  // position of the current byte
-    uint32_t reps[4], rep_lens[4];
+    uint32_t reps[4];
     uint32_t a_byte = 0, b_byte[4] = {1, 1, 1, 1};
     const bool in_range = c + lane < n;
     if (in_range) a_byte = data[c + lane];
@@ -808,27 +808,26 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
         reps[i] = rep_dist[i];
         if (in_range) b_byte[i] = data[c + lane - reps[i] - 1];
     }
-    int rep_max_index = 0;
-    {
-        bool more[4];
+    // The four reps are handled by lanes 0..3, one rep each (one copy of the bitmap arithmetic instead of four);
+    // `my_len` and friends differ per lane, the warp-uniform values are taken from them by shuffle.
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            eq[i] = __ballot_sync(kFull, in_range && a_byte == b_byte[i]);
-            rep_lens[i] = (uint32_t)eq_fast(eq[i], 0, kMatchMaxLen, more[i]);
-        }
-        if (more[0] || more[1] || more[2] || more[3]) {
+    for (int i = 0; i < 4; i++) eq[i] = __ballot_sync(kFull, in_range && a_byte == b_byte[i]);
+    const int ri = lane & 3;
+    uint32_t my_rep = sel4(reps, ri);
+    int my_len;
+    {
+        bool more;
+        my_len = eq_fast(sel4(eq, ri), 0, kMatchMaxLen, more);
 #pragma unroll 1
-            for (int i = 0; i < 4; i++)
-                if (sel4(more, i)) set4(rep_lens, i, (uint32_t)eq_more((int)sel4(rep_lens, i), 0, c, sel4(reps, i), kMatchMaxLen));
+        for (unsigned mm = __ballot_sync(kFull, more && lane < 4); mm; mm &= mm - 1) {
+            const int i = __ffs(mm) - 1;
+            const int v = eq_more(__shfl_sync(kFull, my_len, i), 0, c, __shfl_sync(kFull, my_rep, i), kMatchMaxLen);
+            if (lane == i) my_len = v;
         }
     }
-    uint32_t rep_max_len = rep_lens[0];  // first index of the maximum (:396-398)
-#pragma unroll
-    for (int i = 1; i < 4; i++)
-        if (rep_lens[i] > rep_max_len) {
-            rep_max_index = i;
-            rep_max_len = rep_lens[i];
-        }
+    // first index of the maximum (:396-398)
+    const uint32_t rep_max_len = __reduce_max_sync(kFull, lane < 4 ? (uint32_t)my_len : 0u);
+    const int rep_max_index = __ffs(__ballot_sync(kFull, lane < 4 && (uint32_t)my_len == rep_max_len)) - 1;
     if ((int)rep_max_len >= fb) {  // :400-404
         const int len_res = (int)rep_max_len;
         *back_out = (uint32_t)rep_max_index;
@@ -889,10 +888,11 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
     for (int len = 2 + lane; len <= len_end; len += 32) node(len)->price = kInfinityPrice;  // :451-455
     __syncwarp();
 
+    const int rep0_len = __shfl_sync(kFull, my_len, 0);
     #pragma unroll 1
-    for (int i = 0; i < kNumRepDistances; i++) {  // :457-474, one length per lane
-        const int rep_len = (int)sel4(rep_lens, i);
-        if (rep_len < 2) continue;
+    for (unsigned rm = __ballot_sync(kFull, lane < 4 && my_len >= 2); rm; rm &= rm - 1) {  // :457-474, one length per lane
+        const int i = __ffs(rm) - 1;
+        const int rep_len = __shfl_sync(kFull, my_len, i);
         const uint32_t price = rep_match_price + pure_rep_price(i, st, pos_state);
         #pragma unroll 1
         for (int len = 2 + lane; len <= rep_len; len += 32)
@@ -902,7 +902,7 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
 
     uint32_t normal_match_price = match_price + price0(*p_is_rep(st));
     {
-        const int start = rep_lens[0] >= 2 ? (int)rep_lens[0] + 1 : 2;  // :478-501
+        const int start = rep0_len >= 2 ? rep0_len + 1 : 2;  // :478-501
         #pragma unroll 1
         for (int len = start + lane; len <= len_main; len += 32) {
             int offs = 0;
@@ -1041,41 +1041,39 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
         if (num_avail_full < 2) continue;
 
         // ---- rep lengths and every continuation length, then one extension of the node range
-        int len_test[4], len_test2[4];
+        // lanes 0..3 own one rep each: my_len = lenTest, my_len2 = lenTest2 of that rep (:669-700)
         int need = len_end;
+        my_rep = sel4(reps, ri);
+        int my_len2 = 0;
         {
-            bool more[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) len_test[i] = eq_fast(eq[i], 0, num_avail, more[i]);
-            if (more[0] || more[1] || more[2] || more[3]) {
+            const unsigned my_eq = sel4(eq, ri);
+            bool more;
+            my_len = eq_fast(my_eq, 0, num_avail, more);
 #pragma unroll 1
-                for (int i = 0; i < 4; i++)
-                    if (sel4(more, i)) set4(len_test, i, eq_more(sel4(len_test, i), 0, c, sel4(reps, i), num_avail));
+            for (unsigned mm = __ballot_sync(kFull, more && lane < 4); mm; mm &= mm - 1) {
+                const int i = __ffs(mm) - 1;
+                const int v = eq_more(__shfl_sync(kFull, my_len, i), 0, c, __shfl_sync(kFull, my_rep, i), num_avail);
+                if (lane == i) my_len = v;
             }
-            int lim2[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                len_test2[i] = 0;
-                more[i] = false;
-                lim2[i] = 0;
-                if (len_test[i] >= 2) {
-                    if (cur + len_test[i] > need) need = cur + len_test[i];
-                    if (len_test[i] < num_avail_full) {
-                        lim2[i] = num_avail_full - 1 - len_test[i] < fb ? num_avail_full - 1 - len_test[i] : fb;
-                        len_test2[i] = eq_fast(eq[i], len_test[i] + 1, lim2[i], more[i]);
-                    }
-                }
+            int lim2 = 0;
+            more = false;
+            if (my_len >= 2 && my_len < num_avail_full) {
+                lim2 = num_avail_full - 1 - my_len < fb ? num_avail_full - 1 - my_len : fb;
+                my_len2 = eq_fast(my_eq, my_len + 1, lim2, more);
             }
-            if (more[0] || more[1] || more[2] || more[3]) {
 #pragma unroll 1
-                for (int i = 0; i < 4; i++)
-                    if (sel4(more, i))
-                        set4(len_test2, i, eq_more(sel4(len_test2, i), sel4(len_test, i) + 1, c, sel4(reps, i), sel4(lim2, i)));
+            for (unsigned mm = __ballot_sync(kFull, more && lane < 4); mm; mm &= mm - 1) {
+                const int i = __ffs(mm) - 1;
+                const int v = eq_more(__shfl_sync(kFull, my_len2, i), __shfl_sync(kFull, my_len, i) + 1, c, __shfl_sync(kFull, my_rep, i),
+                                      __shfl_sync(kFull, lim2, i));
+                if (lane == i) my_len2 = v;
             }
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (len_test2[i] >= 2 && cur + len_test[i] + 1 + len_test2[i] > need) need = cur + len_test[i] + 1 + len_test2[i];
+            int my_need = 0;
+            if (lane < 4 && my_len >= 2) my_need = cur + my_len + (my_len2 >= 2 ? 1 + my_len2 : 0);
+            const int rep_need = (int)__reduce_max_sync(kFull, (unsigned)my_need);
+            if (rep_need > need) need = rep_need;
         }
+        const int len_test0 = __shfl_sync(kFull, my_len, 0);
         int lit_rep0_len = 0;
         if (!next_is_char && match_byte != current_byte) {  // :637-641
             const int t = num_avail_full - 1 < fb ? num_avail_full - 1 : fb;
@@ -1084,7 +1082,7 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
             if (more0) lit_rep0_len = eq_more(lit_rep0_len, 1, c, reps[0], t);
             if (lit_rep0_len >= 2 && cur + 1 + lit_rep0_len > need) need = cur + 1 + lit_rep0_len;
         }
-        const int start_len = len_test[0] >= 2 ? len_test[0] + 1 : 2;  // :667, :691-693
+        const int start_len = len_test0 >= 2 ? len_test0 + 1 : 2;  // :667, :691-693
         if (new_len > num_avail) {  // :737-743
             new_len = num_avail;
             #pragma unroll 1
@@ -1124,17 +1122,16 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
         }
 
         // ---- reps (:669-735); most positions have no rep of length >= 2 at all
-        const bool any_rep = len_test[0] >= 2 || len_test[1] >= 2 || len_test[2] >= 2 || len_test[3] >= 2;
 #pragma unroll 1
-        for (int rep_index = 0; any_rep && rep_index < kNumRepDistances; rep_index++) {
-            const int lt = sel4(len_test, rep_index);
-            if (lt < 2) continue;
+        for (unsigned rm = __ballot_sync(kFull, lane < 4 && my_len >= 2); rm; rm &= rm - 1) {
+            const int rep_index = __ffs(rm) - 1;
+            const int lt = __shfl_sync(kFull, my_len, rep_index);
             const uint32_t rp = rep_match_price + pure_rep_price(rep_index, st, pos_state);
             #pragma unroll 1
             for (int len = 2 + lane; len <= lt; len += 32)
                 relax(cur + len, rp + len_price(1, len - 2, pos_state), (uint32_t)cur, (uint32_t)rep_index, false, false, 0, 0);
             __syncwarp();
-            const int lt2 = sel4(len_test2, rep_index);
+            const int lt2 = __shfl_sync(kFull, my_len2, rep_index);
             if (lt2 >= 2) {  // rep + literal + rep0 (:696-734)
                 int state2 = st_longrep(st);
                 uint32_t ps_next = (position + lt) & pos_mask;
@@ -1146,7 +1143,7 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
                 } else {
                     sym = data[c + lt];
                     prv = data[c + lt - 1];
-                    mb = data[c + lt - sel4(reps, rep_index) - 1];
+                    mb = data[c + lt - __shfl_sync(kFull, my_rep, rep_index) - 1];
                 }
                 const uint32_t cur_and_len_char_price = rp + len_price(1, lt - 2, pos_state) + price0(*p_is_match(state2, ps_next)) +
                                                         lit_price(lit_coder(position + lt, prv), true, mb, sym);
