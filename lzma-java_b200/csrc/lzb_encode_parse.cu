@@ -134,16 +134,16 @@ __device__ __forceinline__ void rc_init(RcState* rs, uint8_t* out, uint64_t cap,
         low = (low & 0xFFFFFF) << 8;                                               \
     } while (0)
 
-// Encode `cnt` (<= 32) decisions.  Lane k < cnt passes its decision: `prob` (ignored for a direct
-// bit) and bd = bit | direct << 1.  RangeEncoder.encode :38-54 / encodeDirectBits :56-67.
-__device__ __noinline__ void rc_batch(RcState* rs, int cnt, uint16_t* prob, uint32_t bd, int lane) {
+// Encode `cnt` (<= 32) binary decisions.  Lane k < cnt passes its decision: the probability and the bit.
+// RangeEncoder.encode :38-54.  (Direct bits go through rc_direct: a test for them in this loop cost every decision
+// six issue slots.)
+__device__ __noinline__ void rc_batch(RcState* rs, int cnt, uint16_t* prob, uint32_t bit, int lane) {
     uint32_t p = 0;
-    const uint32_t bit = bd & 1u;
-    if (lane < cnt && !(bd & 2u)) {
+    if (lane < cnt) {
         p = *prob;
         *prob = (uint16_t)(bit ? p - (p >> kNumMoveBits) : p + ((kBitModelTotal - p) >> kNumMoveBits));
     }
-    const uint32_t w = p | (bd << 16);  // old probability | bit << 16 | direct << 17
+    const uint32_t w = p | (bit << 31);  // old probability | bit << 31
     uint64_t low = rs->low;
     uint32_t range = rs->range, cache_size = rs->cache_size, cache = rs->cache, pos = rs->pos;
     const uint32_t cap = rs->cap;
@@ -151,18 +151,38 @@ __device__ __noinline__ void rc_batch(RcState* rs, int cnt, uint16_t* prob, uint
 #pragma unroll 1
     for (int k = 0; k < cnt; k++) {
         const uint32_t e = __shfl_sync(kFull, w, k);
-        if (e & 0x20000u) {
-            range >>= 1;
-            if (e & 0x10000u) low += range;
+        const uint32_t bound = (range >> kNumBitModelTotalBits) * (e & 0xFFFFu);
+        if ((int32_t)e < 0) {
+            low += bound;
+            range -= bound;
         } else {
-            const uint32_t bound = (range >> kNumBitModelTotalBits) * (e & 0xFFFFu);
-            if (e & 0x10000u) {
-                low += bound;
-                range -= bound;
-            } else {
-                range = bound;
-            }
+            range = bound;
         }
+        if (range < kTopValue) {
+            range <<= 8;
+            LZB_SHIFT_LOW();
+        }
+    }
+    if (lane == 0) {
+        rs->low = low;
+        rs->range = range;
+        rs->cache_size = cache_size;
+        rs->cache = cache;
+        rs->pos = pos;
+    }
+    __syncwarp();
+}
+
+// RangeEncoder.encodeDirectBits (:56-67): the low `nbits` bits of `value`, most significant first; uniform arguments.
+__device__ __noinline__ void rc_direct(RcState* rs, uint32_t value, int nbits, int lane) {
+    uint64_t low = rs->low;
+    uint32_t range = rs->range, cache_size = rs->cache_size, cache = rs->cache, pos = rs->pos;
+    const uint32_t cap = rs->cap;
+    uint8_t* out = rs->out;
+#pragma unroll 1
+    for (int i = nbits - 1; i >= 0; i--) {
+        range >>= 1;
+        if ((value >> i) & 1u) low += range;
         if (range < kTopValue) {
             range <<= 8;
             LZB_SHIFT_LOW();
@@ -1222,21 +1242,14 @@ __device__ __forceinline__ void Enc::emit_match(uint32_t ps, int len, uint32_t p
         const int footer_bits = (slot >> 1) - 1;
         const uint32_t base = (2u | (slot & 1)) << footer_bits;
         const uint32_t pos_reduced = pos - base;
-        bool direct = false;
         if (slot < kEndPosModelIndex) {
             if (lane < footer_bits) reverse_decision(lane, model + L.pos_dec + base - slot - 1, pos_reduced, ptr, bit);
-            cnt = footer_bits;
+            rc_batch(&ctx->rc, footer_bits, ptr, bit, lane);
         } else {
-            const int ndirect = footer_bits - kNumAlignBits;  // encodeDirectBits(posReduced >> 4, ndirect): MSB first
-            if (lane < ndirect) {
-                direct = true;
-                bit = ((pos_reduced >> kNumAlignBits) >> (ndirect - 1 - lane)) & 1;
-            } else if (lane < footer_bits) {
-                reverse_decision(lane - ndirect, model + L.pos_align, pos_reduced & kAlignMask, ptr, bit);
-            }
-            cnt = footer_bits;
+            rc_direct(&ctx->rc, pos_reduced >> kNumAlignBits, footer_bits - kNumAlignBits, lane);  // :998-999
+            if (lane < kNumAlignBits) reverse_decision(lane, model + L.pos_align, pos_reduced & kAlignMask, ptr, bit);
+            rc_batch(&ctx->rc, kNumAlignBits, ptr, bit, lane);
         }
-        rc_batch(&ctx->rc, cnt, ptr, bit | ((uint32_t)direct << 1), lane);
     }
 }
 
@@ -1379,8 +1392,12 @@ __device__ __forceinline__ void Enc::run() {
 // kEncWarpsLitSmem streams per SM with the literal coders in shared memory (168 registers), and up
 // to kEncMaxWarps with the literal coders in global memory (L2), which is what lets a wave with more
 // blocks than the first variant's slots keep 12-14 serial chains per SM in flight.
-template <int MAXW, bool PROGRESS>
+// FIXED: lc3 lp0 pb2, the properties of nearly every .lzma stream (and of the reference's defaults, Encoder.java:151-153),
+// as compile-time constants: the probability-model offsets, pos_state masks and literal-coder strides fold into the
+// addressing, which is worth ~200 instructions of a hot path that is bound by instruction fetch.
+template <int MAXW, bool PROGRESS, bool FIXED>
 __global__ void __launch_bounds__(MAXW * 32, 1) lzb_parse_kernel(ParseArgs a) {
+    const int a_lc = FIXED ? 3 : a.lc, a_lp = FIXED ? 0 : a.lp, a_pb = FIXED ? 2 : a.pb;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CtaTables* tables = reinterpret_cast<CtaTables*>(smem_raw);
     init_cta_tables(tables);
@@ -1388,8 +1405,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) lzb_parse_kernel(ParseArgs a) {
     const int warps = blockDim.x >> 5;
     uint8_t* slice = smem_raw + sizeof(CtaTables) + (size_t)warp * a.slice_bytes;
     const size_t slot = (size_t)blockIdx.x * warps + warp;
-    const ModelLayout L = make_layout(a.lc, a.lp, a.pb);
-    const SliceLayout S = make_slice(a.lc, a.lp, a.pb, a.fb, a.lit_in_smem);
+    const ModelLayout L = make_layout(a_lc, a_lp, a_pb);
+    const SliceLayout S = make_slice(a_lc, a_lp, a_pb, a.fb, a.lit_in_smem);
     uint16_t* model = reinterpret_cast<uint16_t*>(slice);
     uint16_t* lit = S.lit_in_smem ? model + L.literal : a.lit_scratch + slot * (size_t)L.n_literal;
     WarpCtx* ctx = reinterpret_cast<WarpCtx*>(slice + S.ctx);
@@ -1402,7 +1419,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) lzb_parse_kernel(ParseArgs a) {
         ctx->align_prices = reinterpret_cast<uint16_t*>(slice + S.align_prices);
         ctx->len_prices = reinterpret_cast<uint16_t*>(slice + S.len_prices);
         ctx->len_counters = reinterpret_cast<int32_t*>(slice + S.len_counters);
-        ctx->pb = a.pb;
+        ctx->pb = a_pb;
         ctx->table_size = a.fb + 1 - kMatchMinLen;
         ctx->dist_table_size = a.dist_table_size;
         ctx->off_len = L.len;
@@ -1431,7 +1448,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) lzb_parse_kernel(ParseArgs a) {
             if (cap >= LZB_KERNEL_HEADER) {
                 if (lane < LZB_KERNEL_HEADER) {
                     uint32_t v;
-                    if (lane == 0) v = (uint32_t)((a.pb * 5 + a.lp) * 9 + a.lc);
+                    if (lane == 0) v = (uint32_t)((a_pb * 5 + a_lp) * 9 + a_lc);
                     else if (lane < 5) v = ((uint32_t)a.dict_size >> (8 * (lane - 1))) & 0xFF;
                     else v = a.eos ? 0xFF : (uint32_t)(((uint64_t)n >> (8 * (lane - 5))) & 0xFF);
                     out[lane] = (uint8_t)v;
@@ -1487,14 +1504,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1) lzb_parse_kernel(ParseArgs a) {
         e.pairs = reinterpret_cast<const uint32_t*>(a.pool + bl.pairs_off);
         e.pairs2 = reinterpret_cast<const uint16_t*>(a.pool + bl.pairs2_off);
         e.lane = lane;
-        e.lc = a.lc;
-        e.lp = a.lp;
-        e.pb = a.pb;
+        e.lc = a_lc;
+        e.lp = a_lp;
+        e.pb = a_pb;
         e.fb = a.fb;
         e.table_size = a.fb + 1 - kMatchMinLen;
         e.dist_table_size = a.dist_table_size;
-        e.pos_mask = (1u << a.pb) - 1;
-        e.lp_mask = (1u << a.lp) - 1;
+        e.pos_mask = (1u << a_pb) - 1;
+        e.lp_mask = (1u << a_lp) - 1;
         e.eos = a.eos;
         e.run<PROGRESS>();
         if (lane == 0) a.out_len[b] = (uint64_t)ctx->rc.pos > cap ? ~0ull : (uint64_t)ctx->rc.pos + header;
@@ -1539,10 +1556,17 @@ size_t parse_opt_bytes_per_slot() { return sizeof(OptNode) * (size_t)kNumOpts; }
 
 cudaError_t launch_parse(const ParseArgs& a, int grid, int warps, cudaStream_t st) {
     const size_t smem = sizeof(CtaTables) + (size_t)warps * a.slice_bytes;
-    // four instances: where the literal coders live x whether anybody listens to ICodeProgress (the test for the
-    // next report sits in the symbol loop: two instructions and a register that cost 3 % on C3 when compiled in)
-    auto kern = a.lit_in_smem ? (a.progress ? lzb_parse_kernel<kEncWarpsLitSmem, true> : lzb_parse_kernel<kEncWarpsLitSmem, false>)
-                              : (a.progress ? lzb_parse_kernel<kEncMaxWarps, true> : lzb_parse_kernel<kEncMaxWarps, false>);
+    // eight instances: where the literal coders live x whether anybody listens to ICodeProgress (the test for the next
+    // report sits in the symbol loop: two instructions and a register that cost 3 % on C3 when compiled in) x FIXED
+    const bool fixed = a.lc == 3 && a.lp == 0 && a.pb == 2;
+    decltype(&lzb_parse_kernel<kEncMaxWarps, false, false>) kern;
+    if (a.lit_in_smem) {
+        kern = a.progress ? (fixed ? lzb_parse_kernel<kEncWarpsLitSmem, true, true> : lzb_parse_kernel<kEncWarpsLitSmem, true, false>)
+                          : (fixed ? lzb_parse_kernel<kEncWarpsLitSmem, false, true> : lzb_parse_kernel<kEncWarpsLitSmem, false, false>);
+    } else {
+        kern = a.progress ? (fixed ? lzb_parse_kernel<kEncMaxWarps, true, true> : lzb_parse_kernel<kEncMaxWarps, true, false>)
+                          : (fixed ? lzb_parse_kernel<kEncMaxWarps, false, true> : lzb_parse_kernel<kEncMaxWarps, false, false>);
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     kern<<<grid, warps * 32, smem, st>>>(a);
