@@ -800,216 +800,118 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
     opt_cur = 0;
     opt_end = 0;
 
-    int len_main;
-    if (longest_found) {
-        len_main = longest_len;
-        longest_found = false;
-    } else {
-        len_main = read_match_distances();
-    }
-    int num_distance_pairs = num_pairs;
-
-    int num_avail = avail() + 1;
-    if (num_avail < 2) {
-        *back_out = kLit;
-        return 1;
-    }
-    if (num_avail > kMatchMaxLen) num_avail = kMatchMaxLen;
-
-    // window bytes and the four rep comparisons, 32 bytes at once (:393-399, limit 273)
-    uint32_t c = m - 1;  // position of the current byte
+    // One loop for the first position of the chunk (:371-503) and the following ones (:505-810): they share the list
+    // read, the window gather, the rep comparisons and the rep lengths, and the parser is bound by instruction fetch, so
+    // one copy of those beats two.  `cur` starts from a zero the compiler cannot see, or it would peel the first
+    // iteration off again.
+    int num_distance_pairs = 0, num_avail = 0;
+    uint32_t c = 0;
     uint32_t reps[4];
-    uint32_t a_byte = 0, b_byte[4] = {1, 1, 1, 1};
-    const bool in_range = c + lane < n;
-    if (in_range) a_byte = data[c + lane];
+    uint32_t a_byte = 0, b_byte[4];
     unsigned eq[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        reps[i] = rep_dist[i];
-        if (in_range) b_byte[i] = data[c + lane - reps[i] - 1];
-    }
-    // The four reps are handled by lanes 0..3, one rep each (one copy of the bitmap arithmetic instead of four);
-    // `my_len` and friends differ per lane, the warp-uniform values are taken from them by shuffle.
-#pragma unroll
-    for (int i = 0; i < 4; i++) eq[i] = __ballot_sync(kFull, in_range && a_byte == b_byte[i]);
-    const int ri = lane & 3;
-    uint32_t my_rep = sel4(reps, ri);
-    int my_len;
-    {
-        bool more;
-        my_len = eq_fast(sel4(eq, ri), 0, kMatchMaxLen, more);
-#pragma unroll 1
-        for (unsigned mm = __ballot_sync(kFull, more && lane < 4); mm; mm &= mm - 1) {
-            const int i = __ffs(mm) - 1;
-            const int v = eq_more(__shfl_sync(kFull, my_len, i), 0, c, __shfl_sync(kFull, my_rep, i), kMatchMaxLen);
-            if (lane == i) my_len = v;
-        }
-    }
-    // first index of the maximum (:396-398)
-    const uint32_t rep_max_len = __reduce_max_sync(kFull, lane < 4 ? (uint32_t)my_len : 0u);
-    const int rep_max_index = __ffs(__ballot_sync(kFull, lane < 4 && (uint32_t)my_len == rep_max_len)) - 1;
-    if ((int)rep_max_len >= fb) {  // :400-404
-        const int len_res = (int)rep_max_len;
-        *back_out = (uint32_t)rep_max_index;
-        move_pos(len_res - 1);
-        return len_res;
-    }
-    if (len_main >= fb) {  // :406-410
-        *back_out = md_dist(num_distance_pairs - 1) + kNumRepDistances;
-        move_pos(len_main - 1);
-        return len_main;
-    }
-
-    uint32_t current_byte = __shfl_sync(kFull, a_byte, 0);
-    uint32_t match_byte = __shfl_sync(kFull, b_byte[0], 0);
-
-    if (len_main < 2 && current_byte != match_byte && rep_max_len < 2) {  // :415-417
-        *back_out = kLit;
-        return 1;
-    }
-
-    uint32_t pos_state = position & pos_mask;
+    const int ri = lane & 3;  // the four reps are handled by lanes 0..3, one rep each: `my_*` differ per lane
+    uint32_t my_rep = 0;
+    int my_len = 0;
+    uint32_t current_byte = 0, match_byte = 0, pos_state = 0, last_byte = 0;
+    uint32_t match_price = 0, rep_match_price = 0, normal_match_price = 0;
     int st = state;
-    uint32_t price1_ = price0(*p_is_match(st, pos_state)) +
-                       lit_price(lit_coder(position, prev_byte), !st_is_char(st), match_byte, current_byte);
-    uint32_t back1 = kLit;  // MakeAsChar
-
-    uint32_t match_price = price1(*p_is_match(st, pos_state));
-    uint32_t rep_match_price = match_price + price1(*p_is_rep(st));
-
-    if (match_byte == current_byte) {  // :430-436
-        const uint32_t short_rep_price = rep_match_price + rep_len1_price(st, pos_state);
-        if (short_rep_price < price1_) {
-            price1_ = short_rep_price;
-            back1 = 0;  // MakeAsShortRep
-        }
-    }
-
-    int len_end = len_main >= (int)rep_max_len ? len_main : (int)rep_max_len;
-    if (len_end < 2) {
-        *back_out = back1;
-        return 1;
-    }
+    int len_end = 0;
     int wb = 0;  // nodes [0, wb) live in gopt, the rest in the ring
-    __syncwarp();
-    if (lane == 0) {
-        OptNode* o0 = node(0);
-        o0->link = (uint32_t)st << 24;
-        o0->backs[0] = reps[0];
-        o0->backs[1] = reps[1];
-        o0->backs[2] = reps[2];
-        o0->backs[3] = reps[3];
-        OptNode* o1 = node(1);
-        o1->price = price1_;
-        o1->back_prev = back1;
-        o1->link = mk_link(0, 0, false, false);
-    }
+    int cur;
+    asm volatile("mov.u32 %0, 0;" : "=r"(cur));
     #pragma unroll 1
-    for (int len = 2 + lane; len <= len_end; len += 32) node(len)->price = kInfinityPrice;  // :451-455
-    __syncwarp();
-
-    const int rep0_len = __shfl_sync(kFull, my_len, 0);
-    #pragma unroll 1
-    for (unsigned rm = __ballot_sync(kFull, lane < 4 && my_len >= 2); rm; rm &= rm - 1) {  // :457-474, one length per lane
-        const int i = __ffs(rm) - 1;
-        const int rep_len = __shfl_sync(kFull, my_len, i);
-        const uint32_t price = rep_match_price + pure_rep_price(i, st, pos_state);
-        #pragma unroll 1
-        for (int len = 2 + lane; len <= rep_len; len += 32)
-            relax(len, price + len_price(1, len - 2, pos_state), 0, (uint32_t)i, false, false, 0, 0);
-        __syncwarp();
-    }
-
-    uint32_t normal_match_price = match_price + price0(*p_is_rep(st));
-    {
-        const int start = rep0_len >= 2 ? rep0_len + 1 : 2;  // :478-501
-        #pragma unroll 1
-        for (int len = start + lane; len <= len_main; len += 32) {
-            int offs = 0;
-            #pragma unroll 1
-            while (len > md_len(offs)) offs++;
-            const uint32_t distance = md_dist(offs);
-            relax(len, normal_match_price + pos_len_price(distance, len, pos_state), 0, distance + kNumRepDistances, false, false,
-                  0, 0);
+    for (;; cur++) {
+        const bool first = cur == 0;
+        if (!first && cur == len_end) break;
+        int new_len;
+        if (first && longest_found) {
+            new_len = longest_len;
+            longest_found = false;
+        } else {
+            new_len = read_match_distances();
         }
-        __syncwarp();
-    }
-
-    int cur = 0;
-    uint32_t last_byte = current_byte;  // data[c] of the previous step
-    #pragma unroll 1
-    for (;;) {  // :505-810
-        cur++;
-        if (cur == len_end) break;
-        int new_len = read_match_distances();
         num_distance_pairs = num_pairs;
-        if (new_len >= fb) {
-            longest_len = new_len;
-            longest_found = true;
-            break;
+        if (first) {
+            if (avail() + 1 < 2) {
+                *back_out = kLit;
+                return 1;
+            }
+        } else {
+            if (new_len >= fb) {
+                longest_len = new_len;
+                longest_found = true;
+                break;
+            }
+            position++;
         }
-        position++;
-        c = m - 1;
+        c = m - 1;  // position of the current byte
 
         // ---- gather: window bytes + rep comparisons; issued before the node logic to overlap latency
         const bool inr = c + lane < n;
         a_byte = 0;
         if (inr) a_byte = data[c + lane];
 
-        // ---- node cur -> state, reps (:518-590)
-        OptNode* oc = node(cur);
-        const uint4 ca = *reinterpret_cast<const uint4*>(oc);  // price, back_prev, back_prev2, link
-        const uint32_t clink = ca.w;
-        uint32_t pos_prev = ln_pos_prev(clink);
-        if (ln_prev1(clink)) {
-            pos_prev--;
-            if (ln_prev2(clink)) {
-                st = ln_state(node((int)ln_pos_prev2(clink))->link);
-                if (ca.z < kNumRepDistances) st = st_longrep(st);
-                else st = st_match(st);
+        uint32_t cur_price = 0;
+        if (first) {
+            st = state;
+#pragma unroll
+            for (int i = 0; i < 4; i++) reps[i] = rep_dist[i];
+        } else {
+            // ---- node cur -> state, reps (:518-590)
+            OptNode* oc = node(cur);
+            const uint4 ca = *reinterpret_cast<const uint4*>(oc);  // price, back_prev, back_prev2, link
+            const uint32_t clink = ca.w;
+            uint32_t pos_prev = ln_pos_prev(clink);
+            if (ln_prev1(clink)) {
+                pos_prev--;
+                if (ln_prev2(clink)) {
+                    st = ln_state(node((int)ln_pos_prev2(clink))->link);
+                    if (ca.z < kNumRepDistances) st = st_longrep(st);
+                    else st = st_match(st);
+                } else {
+                    st = ln_state(node((int)pos_prev)->link);
+                }
+                st = st_lit(st);
             } else {
                 st = ln_state(node((int)pos_prev)->link);
             }
-            st = st_lit(st);
-        } else {
-            st = ln_state(node((int)pos_prev)->link);
-        }
-        if (pos_prev == (uint32_t)cur - 1) {
-            if (ca.y == 0) st = st_shortrep(st);
-            else st = st_lit(st);
-            // reps stay those of the previous step only if that step was cur - 1's node; reload to be exact
-            const uint4 pb_ = *reinterpret_cast<const uint4*>(node((int)pos_prev)->backs);
-            reps[0] = pb_.x; reps[1] = pb_.y; reps[2] = pb_.z; reps[3] = pb_.w;
-        } else {
-            uint32_t pos;
-            if (ln_prev1(clink) && ln_prev2(clink)) {
-                pos_prev = ln_pos_prev2(clink);
-                pos = ca.z;
-                st = st_longrep(st);
+            if (pos_prev == (uint32_t)cur - 1) {
+                if (ca.y == 0) st = st_shortrep(st);
+                else st = st_lit(st);
+                // reps stay those of the previous step only if that step was cur - 1's node; reload to be exact
+                const uint4 pb_ = *reinterpret_cast<const uint4*>(node((int)pos_prev)->backs);
+                reps[0] = pb_.x; reps[1] = pb_.y; reps[2] = pb_.z; reps[3] = pb_.w;
             } else {
-                pos = ca.y;
-                if (pos < kNumRepDistances) st = st_longrep(st);
-                else st = st_match(st);
+                uint32_t pos;
+                if (ln_prev1(clink) && ln_prev2(clink)) {
+                    pos_prev = ln_pos_prev2(clink);
+                    pos = ca.z;
+                    st = st_longrep(st);
+                } else {
+                    pos = ca.y;
+                    if (pos < kNumRepDistances) st = st_longrep(st);
+                    else st = st_match(st);
+                }
+                const uint4 pb_ = *reinterpret_cast<const uint4*>(node((int)pos_prev)->backs);
+                const uint32_t b0 = pb_.x, b1 = pb_.y, b2 = pb_.z, b3 = pb_.w;
+                if (pos < kNumRepDistances) {
+                    if (pos == 0) { reps[0] = b0; reps[1] = b1; reps[2] = b2; reps[3] = b3; }
+                    else if (pos == 1) { reps[0] = b1; reps[1] = b0; reps[2] = b2; reps[3] = b3; }
+                    else if (pos == 2) { reps[0] = b2; reps[1] = b0; reps[2] = b1; reps[3] = b3; }
+                    else { reps[0] = b3; reps[1] = b0; reps[2] = b1; reps[3] = b2; }
+                } else {
+                    reps[0] = pos - kNumRepDistances;
+                    reps[1] = b0;
+                    reps[2] = b1;
+                    reps[3] = b2;
+                }
             }
-            const uint4 pb_ = *reinterpret_cast<const uint4*>(node((int)pos_prev)->backs);
-            const uint32_t b0 = pb_.x, b1 = pb_.y, b2 = pb_.z, b3 = pb_.w;
-            if (pos < kNumRepDistances) {
-                if (pos == 0) { reps[0] = b0; reps[1] = b1; reps[2] = b2; reps[3] = b3; }
-                else if (pos == 1) { reps[0] = b1; reps[1] = b0; reps[2] = b2; reps[3] = b3; }
-                else if (pos == 2) { reps[0] = b2; reps[1] = b0; reps[2] = b1; reps[3] = b3; }
-                else { reps[0] = b3; reps[1] = b0; reps[2] = b1; reps[3] = b2; }
-            } else {
-                reps[0] = pos - kNumRepDistances;
-                reps[1] = b0;
-                reps[2] = b1;
-                reps[3] = b2;
+            if (lane == 0) {
+                oc->link = (clink & ~(0xFu << 24)) | ((uint32_t)st << 24);
+                *reinterpret_cast<uint4*>(oc->backs) = make_uint4(reps[0], reps[1], reps[2], reps[3]);
             }
+            cur_price = ca.x;
         }
-        if (lane == 0) {
-            oc->link = (clink & ~(0xFu << 24)) | ((uint32_t)st << 24);
-            *reinterpret_cast<uint4*>(oc->backs) = make_uint4(reps[0], reps[1], reps[2], reps[3]);
-        }
-        const uint32_t cur_price = ca.x;
 
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -1026,6 +928,103 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
         current_byte = __shfl_sync(kFull, a_byte, 0);
         match_byte = __shfl_sync(kFull, b_byte[0], 0);
         pos_state = position & pos_mask;
+
+        // ---- rep lengths (:393-399 with limit 273 at the first position, :669-690 with numAvailableBytes after it)
+        my_rep = sel4(reps, ri);
+        const unsigned my_eq = sel4(eq, ri);
+        {
+            const int rep_limit = first ? kMatchMaxLen : num_avail;
+            bool more;
+            my_len = eq_fast(my_eq, 0, rep_limit, more);
+#pragma unroll 1
+            for (unsigned mm = __ballot_sync(kFull, more && lane < 4); mm; mm &= mm - 1) {
+                const int i = __ffs(mm) - 1;
+                const int v = eq_more(__shfl_sync(kFull, my_len, i), 0, c, __shfl_sync(kFull, my_rep, i), rep_limit);
+                if (lane == i) my_len = v;
+            }
+        }
+
+        if (first) {
+            const int len_main = new_len;
+            // first index of the maximum (:396-398)
+            const uint32_t rep_max_len = __reduce_max_sync(kFull, lane < 4 ? (uint32_t)my_len : 0u);
+            const int rep_max_index = __ffs(__ballot_sync(kFull, lane < 4 && (uint32_t)my_len == rep_max_len)) - 1;
+            if ((int)rep_max_len >= fb) {  // :400-404
+                const int len_res = (int)rep_max_len;
+                *back_out = (uint32_t)rep_max_index;
+                move_pos(len_res - 1);
+                return len_res;
+            }
+            if (len_main >= fb) {  // :406-410
+                *back_out = md_dist(num_distance_pairs - 1) + kNumRepDistances;
+                move_pos(len_main - 1);
+                return len_main;
+            }
+            if (len_main < 2 && current_byte != match_byte && rep_max_len < 2) {  // :415-417
+                *back_out = kLit;
+                return 1;
+            }
+            uint32_t price1_ = price0(*p_is_match(st, pos_state)) +
+                               lit_price(lit_coder(position, prev_byte), !st_is_char(st), match_byte, current_byte);
+            uint32_t back1 = kLit;  // MakeAsChar
+            match_price = price1(*p_is_match(st, pos_state));
+            rep_match_price = match_price + price1(*p_is_rep(st));
+            if (match_byte == current_byte) {  // :430-436
+                const uint32_t short_rep_price = rep_match_price + rep_len1_price(st, pos_state);
+                if (short_rep_price < price1_) {
+                    price1_ = short_rep_price;
+                    back1 = 0;  // MakeAsShortRep
+                }
+            }
+            len_end = len_main >= (int)rep_max_len ? len_main : (int)rep_max_len;
+            if (len_end < 2) {
+                *back_out = back1;
+                return 1;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                OptNode* o0 = node(0);
+                o0->link = (uint32_t)st << 24;
+                o0->backs[0] = reps[0];
+                o0->backs[1] = reps[1];
+                o0->backs[2] = reps[2];
+                o0->backs[3] = reps[3];
+                OptNode* o1 = node(1);
+                o1->price = price1_;
+                o1->back_prev = back1;
+                o1->link = mk_link(0, 0, false, false);
+            }
+            #pragma unroll 1
+            for (int len = 2 + lane; len <= len_end; len += 32) node(len)->price = kInfinityPrice;  // :451-455
+            __syncwarp();
+
+            const int rep0_len = __shfl_sync(kFull, my_len, 0);
+            #pragma unroll 1
+            for (unsigned rm = __ballot_sync(kFull, lane < 4 && my_len >= 2); rm; rm &= rm - 1) {  // :457-474, one length per lane
+                const int i = __ffs(rm) - 1;
+                const int rep_len = __shfl_sync(kFull, my_len, i);
+                const uint32_t price = rep_match_price + pure_rep_price(i, st, pos_state);
+                #pragma unroll 1
+                for (int len = 2 + lane; len <= rep_len; len += 32)
+                    relax(len, price + len_price(1, len - 2, pos_state), 0, (uint32_t)i, false, false, 0, 0);
+                __syncwarp();
+            }
+
+            normal_match_price = match_price + price0(*p_is_rep(st));
+            const int start = rep0_len >= 2 ? rep0_len + 1 : 2;  // :478-501
+            #pragma unroll 1
+            for (int len = start + lane; len <= len_main; len += 32) {
+                int offs = 0;
+                #pragma unroll 1
+                while (len > md_len(offs)) offs++;
+                const uint32_t distance = md_dist(offs);
+                relax(len, normal_match_price + pos_len_price(distance, len, pos_state), 0, distance + kNumRepDistances, false, false,
+                      0, 0);
+            }
+            __syncwarp();
+            last_byte = current_byte;  // data[c] of the previous step
+            continue;
+        }
 
         // ---- literal and short rep into node cur + 1 (:598-625)
         const uint32_t cur_and1_price = cur_price + price0(*p_is_match(st, pos_state)) +
@@ -1063,20 +1062,10 @@ __device__ __forceinline__ int Enc::get_optimum(uint32_t position, uint32_t* bac
         // ---- rep lengths and every continuation length, then one extension of the node range
         // lanes 0..3 own one rep each: my_len = lenTest, my_len2 = lenTest2 of that rep (:669-700)
         int need = len_end;
-        my_rep = sel4(reps, ri);
         int my_len2 = 0;
         {
-            const unsigned my_eq = sel4(eq, ri);
-            bool more;
-            my_len = eq_fast(my_eq, 0, num_avail, more);
-#pragma unroll 1
-            for (unsigned mm = __ballot_sync(kFull, more && lane < 4); mm; mm &= mm - 1) {
-                const int i = __ffs(mm) - 1;
-                const int v = eq_more(__shfl_sync(kFull, my_len, i), 0, c, __shfl_sync(kFull, my_rep, i), num_avail);
-                if (lane == i) my_len = v;
-            }
             int lim2 = 0;
-            more = false;
+            bool more = false;
             if (my_len >= 2 && my_len < num_avail_full) {
                 lim2 = num_avail_full - 1 - my_len < fb ? num_avail_full - 1 - my_len : fb;
                 my_len2 = eq_fast(my_eq, my_len + 1, lim2, more);
