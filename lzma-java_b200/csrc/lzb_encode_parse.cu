@@ -21,11 +21,17 @@
 //     reach the same node are applied in the reference's order with the
 //     reference's comparison (strict <, one <= for the short rep), so ties
 //     resolve identically (App. A #8);
+//   * the four rep distances of a position belong to lanes 0..3, one each:
+//     rep length, "rep + literal + rep0" length and the node range they need
+//     come from ONE copy of the bitmap arithmetic (the kernel's hot path has
+//     to fit a 32 KB instruction cache: DESIGN.md, parser);
 //   * literal prices use eight lanes, one per bit; price-table refreshes use
 //     one lane per table entry;
-//   * emission (the adaptive range coder) is a serial chain and runs on lane 0.
+//   * a symbol is emitted as a batch: lane k adapts the k-th probability, the
+//     range-coder fold (a serial chain) runs over shuffled (probability, bit)
+//     pairs in every lane and lane 0 stores the bytes.
 // Shared memory per warp: the probability model (pb-strided layout), all
-// price tables as u16, the current match list, and a ring of R = 2^k >= 4 fb + 3
+// price tables as u16, the current match list, and a ring of >= 4 fb + 3
 // packed 32-byte _optimum nodes.  A parse chunk may span 4095 positions, but a
 // step only touches nodes [cur - 2fb - 1, cur + 2fb + 1]; older nodes are
 // written back to global memory and Backward runs there when a chunk wrapped.
