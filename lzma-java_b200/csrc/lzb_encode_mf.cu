@@ -95,8 +95,18 @@ __global__ void __launch_bounds__(128) lzb_mf_link_kernel(MfWave w) {
     uint32_t* head4 = w.bt4 ? heads + kHash2Size + kHash3Size : heads;  // kFixHashSize, BinTree.java:57-69
     const uint32_t min_check = w.bt4 ? 4 : 3;                           // kMinMatchCheck
 
+    // the four bytes at a position, packed; requested one step ahead so that a step waits for one memory round trip (the
+    // table gather) instead of two (window bytes, then the gather)
+    auto load4 = [&](uint32_t q) -> uint32_t {
+        uint32_t v = 0;
+        if (q + 3 < n) v = (uint32_t)data[q] | ((uint32_t)data[q + 1] << 8) | ((uint32_t)data[q + 2] << 16) | ((uint32_t)data[q + 3] << 24);
+        else if (q + 1 < n) v = (uint32_t)data[q] | ((uint32_t)data[q + 1] << 8);  // bt2 hashes two bytes (positions with >= 3 left)
+        return v;
+    };
+    uint32_t cur4 = load4((uint32_t)lane);
     for (uint32_t base = 0; base < n; base += 32) {
         const uint32_t p = base + lane, pos1 = p + 1;
+        const uint32_t nxt4 = load4(p + 32);
         const bool in_range = p < n;
         // positions with lenLimit < kMinMatchCheck are not inserted at all (BinTree.java:158-161)
         const bool valid = in_range && n - p >= min_check;
@@ -104,16 +114,17 @@ __global__ void __launch_bounds__(128) lzb_mf_link_kernel(MfWave w) {
         uint32_t h2 = 0, h3 = 0, h4 = 0;
         LinkStep s2, s3, s4;
         if (valid) {
+            const uint32_t d0 = cur4 & 0xFF, d1 = (cur4 >> 8) & 0xFF, d2 = (cur4 >> 16) & 0xFF, d3 = cur4 >> 24;
             if (w.bt4) {  // BinTree.java:171-175
-                uint32_t t = s_crc[data[p]] ^ data[p + 1];
+                uint32_t t = s_crc[d0] ^ d1;
                 h2 = t & (kHash2Size - 1);
-                t ^= (uint32_t)data[p + 2] << 8;
+                t ^= d2 << 8;
                 h3 = t & (kHash3Size - 1);
-                h4 = (t ^ (s_crc[data[p + 3]] << 5)) & w.hash_mask;
+                h4 = (t ^ (s_crc[d3] << 5)) & w.hash_mask;
                 s2.read(heads, h2, vm, lane);
                 s3.read(head3, h3, vm, lane);
             } else {
-                h4 = data[p] ^ ((uint32_t)data[p + 1] << 8);
+                h4 = d0 ^ (d1 << 8);
             }
             s4.read(head4, h4, vm, lane);
         }
@@ -137,6 +148,7 @@ __global__ void __launch_bounds__(128) lzb_mf_link_kernel(MfWave w) {
             prev2[pos1] = 0;
         }
         __syncwarp();
+        cur4 = nxt4;
     }
 }
 
